@@ -1,0 +1,106 @@
+"""Seeded synthetic graphs / features / weights of the shapes BASELINE.json names.
+
+There is no dataset in the reference tree (./data is a Google-Drive zip) and no
+network, so every parity test and the bench run on synthetic inputs generated here.  The
+generators are plain numpy (host) so that the reference, the oracle and the CUDA path can be fed
+the very same arrays.  The large scale-free graph of config C5 is generated on the device by
+``bench.py`` instead (same Chung-Lu recipe, torch RNG) because 124 M directed entries are too slow
+to build with scipy.
+
+Shapes:
+  C1 twitch-RU : n=4385,  37 304 undirected edges, f=3170, c=2,   T=500
+  C2 PPI       : n=14755, nnz~225K,               f=50,   c=121, T=500 (unbalanced-hi, deg>=30)
+  C3 Flickr    : n=89250, nnz~900K,               f=500,  c=7,   T=2000
+  C5 large     : n=2.45M, 61.9M undirected edges, f=100,  c=47,  T=8192
+"""
+from __future__ import annotations
+
+import dataclasses
+
+import numpy as np
+
+SHAPES = {
+    # name: n, undirected edges, f, c, T, dataset string handed to the samplers, sample_type
+    "twitch": dict(n=4385, m=37304, f=3170, c=2, T=500, dataset="twitch/ES/RU", sample_type="unbalanced"),
+    "ppi": dict(n=14755, m=112500, f=50, c=121, T=500, dataset="ppi", sample_type="unbalanced-hi"),
+    "flickr": dict(n=89250, m=450000, f=500, c=7, T=2000, dataset="flickr", sample_type="unbalanced"),
+    "large": dict(n=2449029, m=61859140, f=100, c=47, T=8192, dataset="large", sample_type="unbalanced"),
+    # tiny variants used by the CPU-side and quick GPU parity tests
+    "tiny": dict(n=300, m=1200, f=24, c=5, T=40, dataset="twitch/ES/RU", sample_type="unbalanced"),
+    "small": dict(n=1500, m=9000, f=70, c=11, T=120, dataset="ppi", sample_type="unbalanced"),
+}
+
+
+def chung_lu_edges(n: int, m: int, rng: np.random.Generator, alpha: float = 0.5) -> np.ndarray:
+    """``m`` distinct undirected edges (u<v) of a power-law expected-degree graph.
+
+    Endpoint i is drawn with probability ∝ (i+1)^-alpha (inverse CDF: i = n·u^(1/(1-alpha))), which
+    gives a degree exponent 1+1/alpha (3 for alpha=0.5) and hubs of degree ~ m/sqrt(n).  Self loops
+    and repeated pairs are discarded and re-drawn, so the graph is simple like the real datasets.
+    """
+    inv = 1.0 / (1.0 - alpha)
+    got = np.empty(0, dtype=np.int64)
+    need = m
+    while need > 0:
+        k = int(need * 1.3) + 16
+        a = np.minimum((n * rng.random(k) ** inv).astype(np.int64), n - 1)
+        b = np.minimum((n * rng.random(k) ** inv).astype(np.int64), n - 1)
+        keep = a != b
+        lo = np.minimum(a[keep], b[keep])
+        hi = np.maximum(a[keep], b[keep])
+        got = np.unique(np.concatenate([got, lo * n + hi]))
+        need = m - got.size
+    if got.size > m:  # drop a seeded random surplus, keep key order
+        got = np.sort(rng.permutation(got)[:m])
+    # scatter node ids so that degree does not correlate with the id (real graphs are not sorted)
+    perm = rng.permutation(n)
+    edges = np.stack([perm[got // n], perm[got % n]], axis=1)
+    return edges
+
+
+@dataclasses.dataclass
+class Synth:
+    name: str
+    n: int
+    f: int
+    c: int
+    T: int
+    dataset: str
+    sample_type: str
+    edges: np.ndarray          # [m, 2] int64, one row per undirected edge (like musae_*_edges.csv)
+    features: np.ndarray       # [n, f] float32
+    hidden: int = 256
+
+
+def make(name: str, seed: int = 0, hidden: int = 256, **override) -> Synth:
+    """Build the synthetic inputs of a named shape (numpy, deterministic in ``seed``)."""
+    cfg = dict(SHAPES[name])
+    cfg.update(override)
+    rng = np.random.default_rng(seed)
+    n, m, f = cfg["n"], cfg["m"], cfg["f"]
+    edges = chung_lu_edges(n, m, rng)
+    if name == "twitch":
+        # binary attributes (~1 % ones) pushed through a StandardScaler, like worker.py:481-484
+        x = (rng.random((n, f)) < 0.01).astype(np.float64)
+        mu = x.mean(0)
+        sd = x.std(0)
+        sd[sd == 0] = 1.0
+        feats = ((x - mu) / sd).astype(np.float32)
+    else:
+        feats = rng.standard_normal((n, f), dtype=np.float32)
+    return Synth(name=name, n=n, f=f, c=cfg["c"], T=cfg["T"], dataset=cfg["dataset"],
+                 sample_type=cfg["sample_type"], edges=edges, features=feats, hidden=hidden)
+
+
+def gcn_weights(f: int, h: int, c: int, seed: int = 42):
+    """Weights with the distribution of GraphConvolution.reset_parameters (gcn/layers.py:24-28):
+    U(-1/sqrt(out), 1/sqrt(out)) for weight [in,out] and bias [out].  numpy RNG (not torch) so the
+    arrays are identical on every box."""
+    rng = np.random.default_rng(seed)
+    s1 = 1.0 / np.sqrt(h)
+    s2 = 1.0 / np.sqrt(c)
+    w1 = rng.uniform(-s1, s1, (f, h)).astype(np.float32)
+    b1 = rng.uniform(-s1, s1, h).astype(np.float32)
+    w2 = rng.uniform(-s2, s2, (h, c)).astype(np.float32)
+    b2 = rng.uniform(-s2, s2, c).astype(np.float32)
+    return w1, b1, w2, b2
