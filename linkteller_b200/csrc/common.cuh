@@ -1,0 +1,133 @@
+// Shared helpers for the linkteller_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "../../include/linkteller_b200.h"
+
+#define LT_WARP 32
+#define LT_FULL 0xffffffffu
+
+namespace lt {
+
+// ---- error reporting: thread-local message, negative int codes across the C ABI ----
+void set_error(const char* fmt, ...);
+
+#define LT_CUDA(expr)                                                                        \
+    do {                                                                                     \
+        cudaError_t _e = (expr);                                                             \
+        if (_e != cudaSuccess) {                                                             \
+            lt::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            return LT_ERR_CUDA;                                                              \
+        }                                                                                    \
+    } while (0)
+
+#define LT_TRY(expr)                 \
+    do {                             \
+        int _s = (expr);             \
+        if (_s != LT_OK) return _s;  \
+    } while (0)
+
+#define LT_CHECK_ARG(cond, msg)                                   \
+    do {                                                          \
+        if (!(cond)) {                                            \
+            lt::set_error("%s:%d: invalid argument: %s", __FILE__, __LINE__, msg); \
+            return LT_ERR_ARG;                                    \
+        }                                                         \
+    } while (0)
+
+#define LT_LAUNCH_CHECK() LT_CUDA(cudaGetLastError())
+
+// ---- stream-ordered scratch memory (freed in reverse order by the destructor) ----
+struct Scratch {
+    cudaStream_t stream;
+    void* ptrs[64];
+    int n = 0;
+    explicit Scratch(cudaStream_t s) : stream(s) {}
+    ~Scratch() {
+        for (int i = n - 1; i >= 0; --i) cudaFreeAsync(ptrs[i], stream);
+    }
+    template <typename T>
+    int alloc(T** out, size_t count) {
+        void* p = nullptr;
+        size_t bytes = count * sizeof(T);
+        if (bytes == 0) bytes = 16;
+        if (n >= 64) {
+            set_error("Scratch: too many allocations");
+            return LT_ERR_INTERNAL;
+        }
+        cudaError_t e = cudaMallocAsync(&p, bytes, stream);
+        if (e != cudaSuccess) {
+            set_error("cudaMallocAsync(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+            return LT_ERR_NOMEM;
+        }
+        ptrs[n++] = p;
+        *out = reinterpret_cast<T*>(p);
+        return LT_OK;
+    }
+};
+
+int device_alloc(void** out, size_t bytes, cudaStream_t s);
+int num_sms();
+
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline int bits_for(uint64_t max_value) {  // number of bits needed to represent max_value
+    int b = 0;
+    while (max_value) { ++b; max_value >>= 1; }
+    return b < 1 ? 1 : b;
+}
+
+// ---- device helpers ----
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(LT_FULL, v, o);
+    return v;
+}
+
+template <typename T>
+__device__ __forceinline__ T warp_inclusive_scan(T v) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        T u = __shfl_up_sync(LT_FULL, v, o);
+        if (lane >= o) v += u;
+    }
+    return v;
+}
+
+// first index in [lo,hi) with a[idx] >= key (a ascending)
+template <typename T, typename K>
+__device__ __forceinline__ int64_t lower_bound(const T* __restrict__ a, int64_t lo, int64_t hi, K key) {
+    while (lo < hi) {
+        int64_t mid = (lo + hi) >> 1;
+        if (a[mid] < key) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+// first index in [lo,hi) with a[idx] > key
+template <typename T, typename K>
+__device__ __forceinline__ int64_t upper_bound(const T* __restrict__ a, int64_t lo, int64_t hi, K key) {
+    while (lo < hi) {
+        int64_t mid = (lo + hi) >> 1;
+        if (a[mid] <= key) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// ---- primitives implemented in scan.cu / radix_sort.cu ----
+// out has n+1 entries: out[0] = 0, out[k] = sum(in[0..k)), out[n] = total.  in may alias out.
+int exclusive_scan_i32(const int32_t* in, int32_t* out, int64_t n, cudaStream_t s);
+int exclusive_scan_i64(const int64_t* in, int64_t* out, int64_t n, cudaStream_t s);
+int exclusive_scan_i32_to_i64(const int32_t* in, int64_t* out, int64_t n, cudaStream_t s);
+
+// Stable LSD radix sort of 64-bit keys over the given bit ranges (8-bit digits), optional 64-bit
+// payload.  Sorted data ends in keys / vals (in place from the caller's view).
+struct BitRange { int begin, end; };
+int radix_sort_u64(uint64_t* keys, uint64_t* vals, int64_t n, const BitRange* ranges, int n_ranges,
+                   cudaStream_t s);
+
+}  // namespace lt

@@ -1,0 +1,614 @@
+// The influence hot path: Attacker.get_gradient_eps_mat (attacker.py:100-108) inside the loop of
+// link_prediction_attack_efficient (attacker.py:209-229), re-derived for the GPU.
+//
+// Perturbing x_v ← (1+δ)x_v changes layer 1 only on N̂(v) = {r : Â[r,v] ≠ 0}:
+//     H'[r] = H[r] + δ·Â[r,v]·P[v],  P = X·W1,  H = Â·P + b1.
+// With ΔR[r] = (relu(H'[r]) − relu(H[r]))/δ and ΔQ[r] = ΔR[r]·W2 (b2 cancels),
+//     ((f(X') − f(X))/δ)[u] = Σ_{r ∈ N̂(v) ∩ N̂(u)} Â[u,r]·ΔQ_v[r],
+// and the influence entry is its 2-norm; everything outside two hops is exactly 0, as in the
+// reference.  Where no ReLU changes sign ΔR[r,k] = Â[r,v]·P[v,k] exactly, so the fp32 cancellation
+// of the reference's finite difference never happens.
+//
+// Work is organised around three sparse structures built per attack ("plan", integer work only):
+//   S : incidences e = (j, r)  for v = test_nodes[lo+j], r ∈ N̂(v)      [CSR by j]  + a_e = Â[r,v]
+//   B : observers  (r → (i, w)) for test node i adjacent to r, w = Â[u_i,r]        [CSR by r ∈ R]
+//   G : records (j, i, e, w) grouped by output pair (j,i), contributions in neighbour order
+// and two numeric kernels:
+//   F1 k_frontier_dq     : ΔQ[e,:] for every incidence      (reads one H row per incidence: HBM-bound
+//                          on large graphs; a [64 x h]·[h x c] register-blocked product per CTA)
+//   F2 k_frontier_reduce : out[j,i] = ‖Σ_k w_k·ΔQ[e_k,:]‖₂  (segmented, deterministic)
+#include "common.cuh"
+
+namespace lt {
+
+int gemm_f32(const float* A, int64_t lda, const int32_t* a_rows, const float* B, int64_t ldb, int transB,
+             const float* bias, int relu, float* C, int64_t ldc, int32_t M, int32_t N, int32_t K, int algo,
+             cudaStream_t s);
+int spmm_csr_f32(const int32_t* indptr, const int32_t* indices, const float* values, const int32_t* rows,
+                 int32_t n_rows, const float* B, int64_t ldb, int32_t d, const float* bias, int relu, float* C,
+                 int64_t ldc, cudaStream_t s);
+
+}  // namespace lt
+
+struct lt_plan {
+    int32_t n = 0, T = 0, lo = 0, hi = 0, Ts = 0;
+    int32_t R = 0;        // |R|
+    int64_t E = 0;        // incidences
+    int64_t NB = 0;       // observer entries
+    int64_t M = 0;        // records
+    int64_t nnzR = 0;     // Σ_{r∈R} nnz(Â[r,:])
+    int32_t* s_indptr = nullptr;  // [Ts+1]
+    int32_t* s_j = nullptr;       // [E] owner row j
+    int32_t* s_rho = nullptr;     // [E] compact index of r in R
+    float* s_a = nullptr;         // [E] Â[r,v]
+    int32_t* rows = nullptr;      // [R] node ids, ascending
+    int32_t* b_indptr = nullptr;  // [R+1]
+    int32_t* b_i = nullptr;       // [NB]
+    float* b_w = nullptr;         // [NB]
+    uint64_t* rec_key = nullptr;  // [M] (j<<32 | i), sorted
+    uint64_t* rec_val = nullptr;  // [M] (e<<32 | float bits of w)
+    int32_t* grp_off = nullptr;   // [M+1] start of every (j,i) group; first n_groups+1 entries valid
+    int32_t* n_groups = nullptr;  // device scalar
+    int32_t n_groups_host = -1;
+    void* owned[16];
+    int n_owned = 0;
+};
+
+namespace lt {
+
+// ------------------------------------------------------------------------------------ plan kernels
+__global__ void k_tmap(const int32_t* __restrict__ test_nodes, int32_t T, int32_t n, int32_t* __restrict__ tmap,
+                       int* __restrict__ err) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= T) return;
+    const int32_t v = test_nodes[i];
+    if (v < 0 || v >= n) { atomicOr(err, 1); return; }
+    if (atomicCAS(&tmap[v], -1, i) != -1) atomicOr(err, 2);  // duplicate test node
+}
+
+// len[i] = nnz of row test_nodes[i] for all T; slice lens go to s_len
+__global__ void k_test_lens(const int32_t* __restrict__ indptr, const int32_t* __restrict__ test_nodes, int32_t T,
+                            int32_t lo, int32_t hi, int32_t* __restrict__ all_len, int32_t* __restrict__ s_len) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= T) return;
+    const int32_t v = test_nodes[i];
+    const int32_t len = indptr[v + 1] - indptr[v];
+    all_len[i] = len;
+    if (i >= lo && i < hi) s_len[i - lo] = len;
+}
+
+// one warp per slice row: flag[r] = 1 for every r in row v
+__global__ void k_mark_rows(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                            const int32_t* __restrict__ test_nodes, int32_t lo, int32_t Ts,
+                            int32_t* __restrict__ flag) {
+    const int lane = threadIdx.x & 31;
+    const int64_t j = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (j >= Ts) return;
+    const int32_t v = test_nodes[lo + j];
+    for (int32_t k = indptr[v] + lane; k < indptr[v + 1]; k += 32) flag[indices[k]] = 1;
+}
+
+// pos = exclusive scan of flag.  rmap[r] = compact index or -1; rows[compact] = r; rlen[compact] = nnz(row r)
+__global__ void k_compact_rows(const int32_t* __restrict__ flag, const int32_t* __restrict__ pos, int32_t n,
+                               const int32_t* __restrict__ indptr, int32_t* __restrict__ rmap,
+                               int32_t* __restrict__ rows, int32_t* __restrict__ rlen) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    if (flag[r]) {
+        const int32_t p = pos[r];
+        rmap[r] = p;
+        rows[p] = (int32_t)r;
+        rlen[p] = indptr[r + 1] - indptr[r];
+    } else {
+        rmap[r] = -1;
+    }
+}
+
+// one warp per slice row j: S entries.  a_e = Â[r,v] looked up in row r (the value the reference's
+// spmm multiplies P'[v] with); a missing entry means Â's pattern is not symmetric.
+__global__ void k_fill_S(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                         const float* __restrict__ values, const int32_t* __restrict__ test_nodes, int32_t lo,
+                         int32_t Ts, const int32_t* __restrict__ rmap, const int32_t* __restrict__ s_indptr,
+                         int32_t* __restrict__ s_j, int32_t* __restrict__ s_rho, float* __restrict__ s_a,
+                         int* __restrict__ err) {
+    const int lane = threadIdx.x & 31;
+    const int64_t j = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (j >= Ts) return;
+    const int32_t v = test_nodes[lo + j];
+    const int32_t beg = indptr[v], len = indptr[v + 1] - beg, dst = s_indptr[j];
+    for (int32_t k = lane; k < len; k += 32) {
+        const int32_t r = indices[beg + k];
+        const int32_t rb = indptr[r], re = indptr[r + 1];
+        const int64_t p = lower_bound(indices, (int64_t)rb, (int64_t)re, v);
+        float a;
+        if (p < re && indices[p] == v) a = values[p];
+        else { a = 0.f; atomicOr(err, 4); }
+        s_j[dst + k] = (int32_t)j;
+        s_rho[dst + k] = rmap[r];
+        s_a[dst + k] = a;
+    }
+}
+
+// observers: one warp per test node i (all T).  MODE 0 counts per frontier row, MODE 1 fills.
+template <int MODE>
+__global__ void k_observers(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                            const float* __restrict__ values, const int32_t* __restrict__ test_nodes, int32_t T,
+                            const int32_t* __restrict__ rmap, int32_t* __restrict__ cnt_or_cursor,
+                            int32_t* __restrict__ b_i, float* __restrict__ b_w) {
+    const int lane = threadIdx.x & 31;
+    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (i >= T) return;
+    const int32_t u = test_nodes[i];
+    for (int32_t k = indptr[u] + lane; k < indptr[u + 1]; k += 32) {
+        const int32_t rho = rmap[indices[k]];
+        if (rho < 0) continue;
+        if (MODE == 0) {
+            atomicAdd(&cnt_or_cursor[rho], 1);
+        } else {
+            const int32_t p = atomicAdd(&cnt_or_cursor[rho], 1);
+            b_i[p] = (int32_t)i;
+            b_w[p] = values[k];
+        }
+    }
+}
+
+__global__ void k_rec_counts(const int32_t* __restrict__ s_rho, int64_t E, const int32_t* __restrict__ b_indptr,
+                             int32_t* __restrict__ rc) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    const int32_t rho = s_rho[e];
+    rc[e] = b_indptr[rho + 1] - b_indptr[rho];
+}
+
+// one warp per incidence: emit its records
+__global__ void k_expand(const int32_t* __restrict__ s_j, const int32_t* __restrict__ s_rho, int64_t E,
+                         const int32_t* __restrict__ b_indptr, const int32_t* __restrict__ b_i,
+                         const float* __restrict__ b_w, const int64_t* __restrict__ rec_off,
+                         uint64_t* __restrict__ key, uint64_t* __restrict__ val) {
+    const int lane = threadIdx.x & 31;
+    const int64_t e = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (e >= E) return;
+    const int32_t rho = s_rho[e];
+    const int32_t b0 = b_indptr[rho], nb = b_indptr[rho + 1] - b0;
+    const int64_t dst = rec_off[e];
+    const uint64_t jhi = (uint64_t)(uint32_t)s_j[e] << 32, ehi = (uint64_t)(uint32_t)e << 32;
+    for (int32_t k = lane; k < nb; k += 32) {
+        key[dst + k] = jhi | (uint32_t)b_i[b0 + k];
+        val[dst + k] = ehi | (uint64_t)__float_as_uint(b_w[b0 + k]);
+    }
+}
+
+__global__ void k_rec_heads(const uint64_t* __restrict__ key, int64_t M, int32_t* __restrict__ head) {
+    int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    head[m] = (m == 0 || key[m] != key[m - 1]) ? 1 : 0;
+}
+// pos = exclusive scan of head (M+1 entries); grp_off[pos[m]] = m for heads, grp_off[total] = M
+__global__ void k_group_offsets(const int32_t* __restrict__ pos, int64_t M, int32_t* __restrict__ grp_off,
+                                int32_t* __restrict__ n_groups) {
+    int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m > M) return;
+    if (m == M) { grp_off[pos[M]] = (int32_t)M; *n_groups = pos[M]; return; }
+    if (pos[m + 1] != pos[m]) grp_off[pos[m]] = (int32_t)m;
+}
+
+// ------------------------------------------------------------------------------------ F1
+constexpr int F1_TILE_E = 64;    // incidences per CTA (8 warps x 8)
+constexpr int F1_HK = 128;       // k-chunk of the hidden dimension held in shared memory
+constexpr int F1_THREADS = 256;
+constexpr int F1_ASTRIDE = F1_HK + 4;
+
+// ΔR chunk → shared (each warp writes and later reads only its own 8 rows), W2 chunk → shared,
+// then acc[8][NC] += ΔR[8 x HK]·W2[HK x 32·NC] with lane ↔ output column.
+template <int NC>
+__global__ void __launch_bounds__(F1_THREADS)
+k_frontier_dq(const int32_t* __restrict__ s_j, const int32_t* __restrict__ s_rho, const float* __restrict__ s_a,
+              int64_t E, const float* __restrict__ H, int64_t ldh, const float* __restrict__ P, int64_t ldp,
+              const int32_t* __restrict__ p_index, const float* __restrict__ W2, int32_t h, int32_t c, int32_t c0,
+              float delta, float inv_delta, float* __restrict__ dq) {
+    extern __shared__ __align__(16) float smem[];
+    float* As = smem;                                   // [F1_TILE_E][F1_ASTRIDE]
+    float* Ws = smem + F1_TILE_E * F1_ASTRIDE;          // [F1_HK][32*NC]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t e0 = (int64_t)blockIdx.x * F1_TILE_E + warp * 8;
+
+    // per-warp incidence metadata (lane q < 8 holds incidence e0+q)
+    int64_t my_h = -1, my_p = -1;
+    float my_a = 0.f;
+    if (lane < 8 && e0 + lane < E) {
+        const int64_t e = e0 + lane;
+        const int32_t j = s_j[e];
+        my_h = (int64_t)s_rho[e] * ldh;
+        my_p = (int64_t)(p_index ? p_index[j] : j) * ldp;
+        my_a = s_a[e];
+    }
+    float acc[8][NC];
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+#pragma unroll
+        for (int m = 0; m < NC; ++m) acc[q][m] = 0.f;
+
+    for (int kc = 0; kc < h; kc += F1_HK) {
+        __syncthreads();  // previous chunk fully consumed before Ws is overwritten
+        // W2 chunk: rows kc..kc+HK, columns c0..c0+32*NC (zero padded)
+        for (int idx = threadIdx.x; idx < F1_HK * 32 * NC; idx += F1_THREADS) {
+            const int kk = idx / (32 * NC), cc = idx % (32 * NC);
+            const int k = kc + kk, col = c0 + cc;
+            Ws[idx] = (k < h && col < c) ? __ldg(W2 + (int64_t)k * c + col) : 0.f;
+        }
+        // ΔR chunk for this warp's 8 incidences; lane covers k = kc + 4*lane .. +3
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int64_t oh = __shfl_sync(LT_FULL, my_h, q);
+            const int64_t op = __shfl_sync(LT_FULL, my_p, q);
+            const float a = __shfl_sync(LT_FULL, my_a, q);
+            float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+            const int k = kc + 4 * lane;
+            if (oh >= 0 && k < h) {   // h % 4 == 0 is a precondition of this kernel
+                const float4 hv = __ldg(reinterpret_cast<const float4*>(H + oh + k));
+                const float4 pv = __ldg(reinterpret_cast<const float4*>(P + op + k));
+                const float da = delta * a;
+                auto dr = [&](float hh, float p) -> float {
+                    const float hp = fmaf(da, p, hh);           // H'[r,k]
+                    if (hh > 0.f) return hp > 0.f ? a * p : -hh * inv_delta;
+                    return hp > 0.f ? hp * inv_delta : 0.f;
+                };
+                t.x = dr(hv.x, pv.x); t.y = dr(hv.y, pv.y); t.z = dr(hv.z, pv.z); t.w = dr(hv.w, pv.w);
+            }
+            *reinterpret_cast<float4*>(As + (warp * 8 + q) * F1_ASTRIDE + 4 * lane) = t;
+        }
+        __syncthreads();
+#pragma unroll 2
+        for (int k = 0; k < F1_HK; k += 4) {
+            float4 av[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) av[q] = *reinterpret_cast<const float4*>(As + (warp * 8 + q) * F1_ASTRIDE + k);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                float b[NC];
+#pragma unroll
+                for (int m = 0; m < NC; ++m) b[m] = Ws[(k + kk) * 32 * NC + lane + 32 * m];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const float a = kk == 0 ? av[q].x : kk == 1 ? av[q].y : kk == 2 ? av[q].z : av[q].w;
+#pragma unroll
+                    for (int m = 0; m < NC; ++m) acc[q][m] = fmaf(a, b[m], acc[q][m]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const int64_t e = e0 + q;
+        if (e >= E) break;
+#pragma unroll
+        for (int m = 0; m < NC; ++m) {
+            const int col = c0 + lane + 32 * m;
+            if (col < c) dq[e * c + col] = acc[q][m];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------ F2
+// G lanes per output pair.  out[j,i] = sqrt(Σ_col (Σ_k w_k·ΔQ[e_k,col])²)
+template <int G>
+__global__ void __launch_bounds__(256)
+k_frontier_reduce(const uint64_t* __restrict__ key, const uint64_t* __restrict__ val,
+                  const int32_t* __restrict__ grp_off, const int32_t* __restrict__ n_groups,
+                  const float* __restrict__ dq, int32_t c, float* __restrict__ out, int64_t ldo) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t g = t / G;
+    const int sub = (int)(t % G);
+    const bool valid = g < *n_groups;
+    float ss = 0.f;
+    uint64_t k0 = 0;
+    if (valid) {
+        const int32_t m0 = grp_off[g], m1 = grp_off[g + 1];
+        k0 = key[m0];
+        for (int col = sub; col < c; col += G) {
+            float z = 0.f;
+            for (int32_t m = m0; m < m1; ++m) {
+                const uint64_t v = val[m];
+                z = fmaf(__uint_as_float((uint32_t)v), dq[(int64_t)(v >> 32) * c + col], z);
+            }
+            ss = fmaf(z, z, ss);
+        }
+    }
+#pragma unroll
+    for (int o = 1; o < G; o <<= 1) ss += __shfl_xor_sync(LT_FULL, ss, o);
+    if (valid && sub == 0) out[(int64_t)(k0 >> 32) * ldo + (int64_t)(k0 & 0xffffffffu)] = sqrtf(ss);
+}
+
+static int plan_own(lt_plan* p, void* ptr) {
+    if (p->n_owned >= 16) { set_error("plan: too many buffers"); return LT_ERR_INTERNAL; }
+    p->owned[p->n_owned++] = ptr;
+    return LT_OK;
+}
+template <typename T>
+static int plan_alloc(lt_plan* p, T** out, size_t count, cudaStream_t s) {
+    void* q = nullptr;
+    size_t bytes = count * sizeof(T);
+    if (bytes == 0) bytes = 16;
+    cudaError_t e = cudaMallocAsync(&q, bytes, s);
+    if (e != cudaSuccess) { set_error("plan: cudaMallocAsync(%zu) failed: %s", bytes, cudaGetErrorString(e)); return LT_ERR_NOMEM; }
+    *out = reinterpret_cast<T*>(q);
+    return plan_own(p, q);
+}
+
+static int plan_build(lt_plan* p, const int32_t* indptr, const int32_t* indices, const float* values,
+                      const int32_t* test_nodes, cudaStream_t s) {
+    const int32_t n = p->n, T = p->T, lo = p->lo, Ts = p->Ts;
+    Scratch scratch(s);
+    int32_t *tmap, *rmap, *flag, *all_len, *rlen;
+    int* err;
+    int64_t* sums;  // [0]=Σ all_len  [1]=Σ rlen
+    LT_TRY(scratch.alloc(&tmap, (size_t)n));
+    LT_TRY(scratch.alloc(&rmap, (size_t)n));
+    LT_TRY(scratch.alloc(&flag, (size_t)n + 1));
+    LT_TRY(scratch.alloc(&all_len, (size_t)T + 1));
+    LT_TRY(scratch.alloc(&err, 1));
+    LT_TRY(scratch.alloc(&sums, 2));
+    LT_TRY(plan_alloc(p, &p->s_indptr, (size_t)Ts + 1, s));
+    LT_CUDA(cudaMemsetAsync(tmap, 0xff, (size_t)n * 4, s));
+    LT_CUDA(cudaMemsetAsync(flag, 0, ((size_t)n + 1) * 4, s));
+    LT_CUDA(cudaMemsetAsync(err, 0, sizeof(int), s));
+    k_tmap<<<(unsigned)ceil_div(T, 256), 256, 0, s>>>(test_nodes, T, n, tmap, err);
+    LT_LAUNCH_CHECK();
+    int herr = 0;
+    LT_CUDA(cudaMemcpyAsync(&herr, err, sizeof(int), cudaMemcpyDeviceToHost, s));
+    LT_CUDA(cudaStreamSynchronize(s));   // test nodes must be valid before they index indptr
+    if (herr & 1) { set_error("lt_plan_create: test node outside [0,%d)", n); return LT_ERR_DATA; }
+    if (herr & 2) { set_error("lt_plan_create: duplicate test node"); return LT_ERR_DATA; }
+    k_test_lens<<<(unsigned)ceil_div(T, 256), 256, 0, s>>>(indptr, test_nodes, T, lo, p->hi, all_len, p->s_indptr);
+    LT_LAUNCH_CHECK();
+    LT_TRY(exclusive_scan_i32(all_len, all_len, T, s));
+    LT_TRY(exclusive_scan_i32(p->s_indptr, p->s_indptr, Ts, s));
+    k_mark_rows<<<(unsigned)ceil_div((int64_t)Ts * 32, 256), 256, 0, s>>>(indptr, indices, test_nodes, lo, Ts, flag);
+    LT_LAUNCH_CHECK();
+    int32_t* pos;
+    LT_TRY(scratch.alloc(&pos, (size_t)n + 1));
+    LT_TRY(exclusive_scan_i32(flag, pos, n, s));
+    int32_t h3[3];
+    LT_CUDA(cudaMemcpyAsync(&h3[0], p->s_indptr + Ts, 4, cudaMemcpyDeviceToHost, s));
+    LT_CUDA(cudaMemcpyAsync(&h3[1], pos + n, 4, cudaMemcpyDeviceToHost, s));
+    LT_CUDA(cudaMemcpyAsync(&h3[2], all_len + T, 4, cudaMemcpyDeviceToHost, s));
+    LT_CUDA(cudaStreamSynchronize(s));
+    p->E = h3[0];
+    p->R = h3[1];
+    const int64_t nb_cap = h3[2];
+    const int32_t R = p->R;
+    const int64_t E = p->E;
+
+    LT_TRY(plan_alloc(p, &p->rows, (size_t)R, s));
+    LT_TRY(scratch.alloc(&rlen, (size_t)R + 1));
+    k_compact_rows<<<(unsigned)ceil_div(n, 256), 256, 0, s>>>(flag, pos, n, indptr, rmap, p->rows, rlen);
+    LT_LAUNCH_CHECK();
+    LT_TRY(plan_alloc(p, &p->s_j, (size_t)E, s));
+    LT_TRY(plan_alloc(p, &p->s_rho, (size_t)E, s));
+    LT_TRY(plan_alloc(p, &p->s_a, (size_t)E, s));
+    k_fill_S<<<(unsigned)ceil_div((int64_t)Ts * 32, 256), 256, 0, s>>>(indptr, indices, values, test_nodes, lo, Ts, rmap,
+                                                                    p->s_indptr, p->s_j, p->s_rho, p->s_a, err);
+    LT_LAUNCH_CHECK();
+
+    // observers
+    int32_t* cursor;
+    LT_TRY(plan_alloc(p, &p->b_indptr, (size_t)R + 1, s));
+    LT_TRY(scratch.alloc(&cursor, (size_t)R + 1));
+    LT_TRY(plan_alloc(p, &p->b_i, (size_t)nb_cap, s));
+    LT_TRY(plan_alloc(p, &p->b_w, (size_t)nb_cap, s));
+    LT_CUDA(cudaMemsetAsync(p->b_indptr, 0, ((size_t)R + 1) * 4, s));
+    const unsigned blT = (unsigned)ceil_div((int64_t)T * 32, 256);
+    k_observers<0><<<blT, 256, 0, s>>>(indptr, indices, values, test_nodes, T, rmap, p->b_indptr, nullptr, nullptr);
+    LT_LAUNCH_CHECK();
+    LT_TRY(exclusive_scan_i32(p->b_indptr, p->b_indptr, R, s));
+    LT_CUDA(cudaMemcpyAsync(cursor, p->b_indptr, ((size_t)R + 1) * 4, cudaMemcpyDeviceToDevice, s));
+    k_observers<1><<<blT, 256, 0, s>>>(indptr, indices, values, test_nodes, T, rmap, cursor, p->b_i, p->b_w);
+    LT_LAUNCH_CHECK();
+
+    // records
+    int32_t* rc;
+    int64_t* rec_off;
+    LT_TRY(scratch.alloc(&rc, (size_t)E + 1));
+    LT_TRY(scratch.alloc(&rec_off, (size_t)E + 1));
+    if (E) {
+        k_rec_counts<<<(unsigned)ceil_div(E, 256), 256, 0, s>>>(p->s_rho, E, p->b_indptr, rc);
+        LT_LAUNCH_CHECK();
+    }
+    LT_TRY(exclusive_scan_i32_to_i64(rc, rec_off, E, s));
+    LT_TRY(exclusive_scan_i32(rlen, rlen, R, s));   // Σ nnz of frontier rows (for the byte accounting)
+    int64_t hM = 0;
+    int32_t hNB = 0, hnnzR = 0;
+    LT_CUDA(cudaMemcpyAsync(&hM, rec_off + E, 8, cudaMemcpyDeviceToHost, s));
+    LT_CUDA(cudaMemcpyAsync(&hNB, p->b_indptr + R, 4, cudaMemcpyDeviceToHost, s));
+    LT_CUDA(cudaMemcpyAsync(&hnnzR, rlen + R, 4, cudaMemcpyDeviceToHost, s));
+    LT_CUDA(cudaMemcpyAsync(&herr, err, sizeof(int), cudaMemcpyDeviceToHost, s));
+    LT_CUDA(cudaStreamSynchronize(s));
+    if (herr & 4) {
+        set_error("lt_plan_create: Â[r,v] missing for a stored Â[v,r] — the adjacency pattern is not symmetric");
+        return LT_ERR_DATA;
+    }
+    p->M = hM;
+    p->NB = hNB;
+    p->nnzR = hnnzR;
+    if (hM >= ((int64_t)1 << 31)) { set_error("lt_plan_create: %lld records exceed 2^31", (long long)hM); return LT_ERR_CAPACITY; }
+    const int64_t M = hM;
+    LT_TRY(plan_alloc(p, &p->rec_key, (size_t)M, s));
+    LT_TRY(plan_alloc(p, &p->rec_val, (size_t)M, s));
+    LT_TRY(plan_alloc(p, &p->grp_off, (size_t)M + 2, s));
+    LT_TRY(plan_alloc(p, &p->n_groups, 1, s));
+    LT_CUDA(cudaMemsetAsync(p->n_groups, 0, 4, s));
+    if (M) {
+        k_expand<<<(unsigned)ceil_div(E * 32, 256), 256, 0, s>>>(p->s_j, p->s_rho, E, p->b_indptr, p->b_i, p->b_w,
+                                                               rec_off, p->rec_key, p->rec_val);
+        LT_LAUNCH_CHECK();
+        BitRange ranges[2] = {{0, bits_for((uint64_t)(T - 1))}, {32, 32 + bits_for((uint64_t)(Ts > 1 ? Ts - 1 : 1))}};
+        LT_TRY(radix_sort_u64(p->rec_key, p->rec_val, M, ranges, Ts > 1 ? 2 : 1, s));
+        int32_t* head;
+        LT_TRY(scratch.alloc(&head, (size_t)M + 1));
+        k_rec_heads<<<(unsigned)ceil_div(M, 256), 256, 0, s>>>(p->rec_key, M, head);
+        LT_LAUNCH_CHECK();
+        LT_TRY(exclusive_scan_i32(head, head, M, s));
+        k_group_offsets<<<(unsigned)ceil_div(M + 1, 256), 256, 0, s>>>(head, M, p->grp_off, p->n_groups);
+        LT_LAUNCH_CHECK();
+    }
+    return LT_OK;
+}
+
+int influence_rows(const lt_plan* p, const float* H_R, int64_t ldh, const float* P, int64_t ldp,
+                   const int32_t* p_index, const float* W2, int32_t h, int32_t c, float delta, float* out,
+                   int64_t ldo, cudaStream_t s) {
+    const int64_t E = p->E, M = p->M;
+    LT_CUDA(cudaMemset2DAsync(out, (size_t)ldo * 4, 0, (size_t)p->T * 4, (size_t)p->Ts, s));
+    if (E == 0 || M == 0) return LT_OK;
+    if (h % 4 != 0 || ldh % 4 != 0 || ldp % 4 != 0 || (uintptr_t)H_R % 16 || (uintptr_t)P % 16) {
+        set_error("lt_influence_rows: h, ldh, ldp must be multiples of 4 and H_R, P 16-byte aligned");
+        return LT_ERR_ARG;
+    }
+    Scratch scratch(s);
+    float* dq;
+    LT_TRY(scratch.alloc(&dq, (size_t)E * c));
+    const unsigned bl = (unsigned)ceil_div(E, F1_TILE_E);
+    const float inv_delta = 1.0f / delta;
+    for (int32_t c0 = 0; c0 < c; c0 += 128) {
+        const int32_t cw = c - c0 < 128 ? c - c0 : 128;
+        const int nc = (cw + 31) / 32;
+        const size_t smem = ((size_t)F1_TILE_E * F1_ASTRIDE + (size_t)F1_HK * 32 * nc) * sizeof(float);
+#define LT_F1(NC_)                                                                                             \
+    do {                                                                                                       \
+        LT_CUDA(cudaFuncSetAttribute(k_frontier_dq<NC_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        k_frontier_dq<NC_><<<bl, F1_THREADS, smem, s>>>(p->s_j, p->s_rho, p->s_a, E, H_R, ldh, P, ldp, p_index, W2, h, \
+                                                        c, c0, delta, inv_delta, dq);                          \
+    } while (0)
+        if (nc == 1) LT_F1(1);
+        else if (nc == 2) LT_F1(2);
+        else if (nc == 3) LT_F1(3);
+        else LT_F1(4);
+#undef LT_F1
+        LT_LAUNCH_CHECK();
+    }
+#define LT_F2(G_)                                                                                              \
+    k_frontier_reduce<G_><<<(unsigned)ceil_div(M * G_, 256), 256, 0, s>>>(p->rec_key, p->rec_val, p->grp_off,  \
+                                                                          p->n_groups, dq, c, out, ldo)
+    if (c <= 1) LT_F2(1);
+    else if (c <= 2) LT_F2(2);
+    else if (c <= 4) LT_F2(4);
+    else if (c <= 8) LT_F2(8);
+    else if (c <= 16) LT_F2(16);
+    else LT_F2(32);
+#undef LT_F2
+    LT_LAUNCH_CHECK();
+    return LT_OK;
+}
+
+static void plan_info(const lt_plan* p, int32_t h, int32_t c, int64_t* info) {
+    info[0] = p->R;
+    info[1] = p->E;
+    info[2] = p->NB;
+    info[3] = p->M;
+    info[4] = p->n_groups_host;
+    // algorithmic bytes of lt_influence_rows: per incidence one H row + (j,ρ,a) + ΔQ written and
+    // read back once; P rows of the slice; per record key+payload; the dense output rows.
+    info[5] = p->E * ((int64_t)4 * h + 12 + 8 * (int64_t)c) + (int64_t)p->Ts * 4 * h + p->M * 16 +
+              (int64_t)p->Ts * p->T * 4;
+    info[6] = p->nnzR;
+    info[7] = 0;
+}
+
+}  // namespace lt
+
+using namespace lt;
+
+extern "C" int lt_plan_create(const int32_t* indptr, const int32_t* indices, const float* values, int32_t n,
+                              const int32_t* test_nodes, int32_t T, int32_t lo, int32_t hi, lt_stream_t stream,
+                              lt_plan** plan_host) {
+    LT_CHECK_ARG(indptr && indices && values && test_nodes && plan_host, "lt_plan_create: null pointer");
+    LT_CHECK_ARG(n > 0 && T > 0 && lo >= 0 && hi >= lo && hi <= T, "lt_plan_create: need 0 <= lo <= hi <= T");
+    cudaStream_t s = (cudaStream_t)stream;
+    lt_plan* p = new lt_plan();
+    p->n = n; p->T = T; p->lo = lo; p->hi = hi; p->Ts = hi - lo;
+    int st = plan_build(p, indptr, indices, values, test_nodes, s);
+    if (st != LT_OK) { lt_plan_destroy(p, stream); return st; }
+    *plan_host = p;
+    return LT_OK;
+}
+
+extern "C" int lt_plan_destroy(lt_plan* plan, lt_stream_t stream) {
+    if (!plan) return LT_OK;
+    for (int i = plan->n_owned - 1; i >= 0; --i) cudaFreeAsync(plan->owned[i], (cudaStream_t)stream);
+    delete plan;
+    return LT_OK;
+}
+
+extern "C" int lt_plan_info(const lt_plan* plan, int32_t h, int32_t c, int64_t* info_host, lt_stream_t stream) {
+    LT_CHECK_ARG(plan && info_host, "lt_plan_info");
+    cudaStream_t s = (cudaStream_t)stream;
+    lt_plan* p = const_cast<lt_plan*>(plan);
+    if (p->n_groups_host < 0) {
+        int32_t g = 0;
+        LT_CUDA(cudaMemcpyAsync(&g, p->n_groups, 4, cudaMemcpyDeviceToHost, s));
+        LT_CUDA(cudaStreamSynchronize(s));
+        p->n_groups_host = g;
+    }
+    plan_info(p, h, c, info_host);
+    return LT_OK;
+}
+
+extern "C" const int32_t* lt_plan_rows(const lt_plan* plan) { return plan ? plan->rows : nullptr; }
+
+extern "C" int lt_plan_copy_rows(const lt_plan* plan, int32_t* dst, lt_stream_t stream) {
+    LT_CHECK_ARG(plan && dst, "lt_plan_copy_rows");
+    LT_CUDA(cudaMemcpyAsync(dst, plan->rows, (size_t)plan->R * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return LT_OK;
+}
+
+extern "C" int lt_influence_rows(const lt_plan* plan, const float* H_R, int64_t ldh, const float* P, int64_t ldp,
+                                 const int32_t* p_index, const float* W2, int32_t h, int32_t c, float delta,
+                                 float* out, int64_t ldo, lt_stream_t stream) {
+    LT_CHECK_ARG(plan && H_R && P && W2 && out, "lt_influence_rows: null pointer");
+    LT_CHECK_ARG(h > 0 && c > 0 && delta != 0.f && ldo >= plan->T && ldh >= h && ldp >= h, "lt_influence_rows: sizes");
+    return influence_rows(plan, H_R, ldh, P, ldp, p_index, W2, h, c, delta, out, ldo, (cudaStream_t)stream);
+}
+
+// plan + restricted precompute + frontier in one call (the whole timed hot path of one rank)
+extern "C" int lt_attack_efficient(const int32_t* indptr, const int32_t* indices, const float* values, int32_t n,
+                                   const float* X, int64_t ldx, int32_t f, const float* W1, const float* b1,
+                                   const float* W2, int32_t h, int32_t c, const int32_t* test_nodes, int32_t T,
+                                   int32_t lo, int32_t hi, float delta, float* out, int64_t ldo, int64_t* info_host,
+                                   lt_stream_t stream) {
+    LT_CHECK_ARG(X && W1 && b1 && W2 && out, "lt_attack_efficient: null pointer");
+    LT_CHECK_ARG(f > 0 && h > 0 && c > 0 && ldx >= f && h % 4 == 0, "lt_attack_efficient: sizes (h % 4 == 0)");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (hi == lo) return LT_OK;
+    lt_plan* plan = nullptr;
+    LT_TRY(lt_plan_create(indptr, indices, values, n, test_nodes, T, lo, hi, stream, &plan));
+    int st = LT_OK;
+    {
+        Scratch scratch(s);
+        const int32_t R = plan->R, Ts = plan->Ts;
+        float *HR = nullptr, *Pt = nullptr;
+        st = scratch.alloc(&HR, (size_t)R * h);
+        if (st == LT_OK) st = scratch.alloc(&Pt, (size_t)Ts * h);
+        // P_v = X[v]·W1 for the slice (gathered rows)
+        if (st == LT_OK) st = gemm_f32(X, ldx, test_nodes + lo, W1, h, 0, nullptr, 0, Pt, h, Ts, h, f, 0, s);
+        const bool aggregate_first = (f < h) && (f % 4 == 0) && (ldx % 4 == 0) && ((uintptr_t)X % 16 == 0);
+        if (st == LT_OK) {
+            if (aggregate_first) {
+                // H_R = (Â[R,:]·X)·W1 + b1 : gathers f floats per non-zero instead of h
+                float* AX = nullptr;
+                st = scratch.alloc(&AX, (size_t)R * f);
+                if (st == LT_OK) st = spmm_csr_f32(indptr, indices, values, plan->rows, R, X, ldx, f, nullptr, 0, AX, f, s);
+                if (st == LT_OK) st = gemm_f32(AX, f, nullptr, W1, h, 0, b1, 0, HR, h, R, h, f, 0, s);
+            } else {
+                // H_R = Â[R,:]·(X·W1) + b1
+                float* Pfull = nullptr;
+                st = scratch.alloc(&Pfull, (size_t)n * h);
+                if (st == LT_OK) st = gemm_f32(X, ldx, nullptr, W1, h, 0, nullptr, 0, Pfull, h, n, h, f, 0, s);
+                if (st == LT_OK) st = spmm_csr_f32(indptr, indices, values, plan->rows, R, Pfull, h, h, b1, 0, HR, h, s);
+            }
+        }
+        if (st == LT_OK) st = influence_rows(plan, HR, h, Pt, h, nullptr, W2, h, c, delta, out, ldo, s);
+        if (st == LT_OK && info_host) st = lt_plan_info(plan, h, c, info_host, stream);
+    }
+    lt_plan_destroy(plan, stream);
+    return st;
+}

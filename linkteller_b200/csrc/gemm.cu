@@ -1,0 +1,153 @@
+// Dense fp32 GEMM  C[M,N] = A[M,K]·B (+bias) (ReLU) — torch.mm in GraphConvolution.forward
+// (gcn/layers.py:31), with an optional row gather on A (P_v = X[v]·W1 for the sampled nodes) and
+// an optional transposed B (LSA2 Gram matrix).
+//
+// algo 1: fp32 SIMT, 128x64x32 tiles, 8x4 register blocking, register-staged double buffering.
+// algo 2: 3xTF32 on the 5th-gen tensor cores (tcgen05.mma kind::tf32, TMEM accumulators) — see
+//         gemm_tc.cu; falls back to algo 1 for shapes it does not cover.
+#include "common.cuh"
+
+namespace lt {
+
+int gemm_3xtf32(const float* A, int64_t lda, const int32_t* a_rows, const float* B, int64_t ldb, int transB,
+                const float* bias, int relu, float* C, int64_t ldc, int32_t M, int32_t N, int32_t K,
+                cudaStream_t s, bool* handled);
+
+constexpr int GM_BM = 128, GM_BN = 64, GM_BK = 32, GM_THREADS = 256;
+constexpr int GM_APAD = 4;
+
+template <bool TRANSB>
+__global__ void __launch_bounds__(GM_THREADS)
+k_gemm_simt(const float* __restrict__ A, int64_t lda, const int32_t* __restrict__ a_rows, const float* __restrict__ B,
+            int64_t ldb, const float* __restrict__ bias, int relu, float* __restrict__ C, int64_t ldc, int M, int N,
+            int K) {
+    __shared__ __align__(16) float As[GM_BK][GM_BM + GM_APAD];  // As[k][m]
+    __shared__ __align__(16) float Bs[GM_BK][GM_BN];            // Bs[k][n]
+    const int tid = threadIdx.x;
+    const int m0 = blockIdx.y * GM_BM, n0 = blockIdx.x * GM_BN;
+    const int ty = tid >> 4, tx = tid & 15;  // 16 x 16 threads → 8 rows x 4 cols each
+
+    // global → register staging.  A tile: 128 rows x 32 k; a warp reads 32 consecutive k of one row.
+    const int a_k = tid & 31, a_r0 = tid >> 5;  // rows a_r0 + 8*i, i<16
+    int64_t a_off[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int m = m0 + a_r0 + 8 * i;
+        a_off[i] = m < M ? (int64_t)(a_rows ? a_rows[m] : m) * lda : -1;
+    }
+    float ra[16], rb[8];
+    auto load_tiles = [&](int k0) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int k = k0 + a_k;
+            ra[i] = (a_off[i] >= 0 && k < K) ? __ldg(A + a_off[i] + k) : 0.f;
+        }
+        if (!TRANSB) {  // B[K,N]: a warp reads 32 consecutive n of one k (two k rows per 64-wide tile pass)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int idx = tid + i * GM_THREADS;       // 0..2047
+                const int k = k0 + (idx >> 6), nn = n0 + (idx & 63);
+                rb[i] = (k < K && nn < N) ? __ldg(B + (int64_t)k * ldb + nn) : 0.f;
+            }
+        } else {        // B stored [N,K]: read 32 consecutive k of one n
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int idx = tid + i * GM_THREADS;
+                const int nn = n0 + (idx >> 5), k = k0 + (idx & 31);
+                rb[i] = (k < K && nn < N) ? __ldg(B + (int64_t)nn * ldb + k) : 0.f;
+            }
+        }
+    };
+    auto store_tiles = [&]() {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) As[a_k][a_r0 + 8 * i] = ra[i];
+        if (!TRANSB) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int idx = tid + i * GM_THREADS;
+                Bs[idx >> 6][idx & 63] = rb[i];
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int idx = tid + i * GM_THREADS;
+                Bs[idx & 31][idx >> 5] = rb[i];
+            }
+        }
+    };
+
+    float acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    load_tiles(0);
+    for (int k0 = 0; k0 < K; k0 += GM_BK) {
+        store_tiles();
+        __syncthreads();
+        if (k0 + GM_BK < K) load_tiles(k0 + GM_BK);
+#pragma unroll
+        for (int k = 0; k < GM_BK; ++k) {
+            const float4 a0 = *reinterpret_cast<const float4*>(&As[k][ty * 8]);
+            const float4 a1 = *reinterpret_cast<const float4*>(&As[k][ty * 8 + 4]);
+            const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+            const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int m = m0 + ty * 8 + i;
+        if (m >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int nn = n0 + tx * 4 + j;
+            if (nn >= N) continue;
+            float v = acc[i][j];
+            if (bias) v += __ldg(bias + nn);
+            if (relu) v = fmaxf(v, 0.f);
+            C[(int64_t)m * ldc + nn] = v;
+        }
+    }
+}
+
+int gemm_f32(const float* A, int64_t lda, const int32_t* a_rows, const float* B, int64_t ldb, int transB,
+             const float* bias, int relu, float* C, int64_t ldc, int32_t M, int32_t N, int32_t K, int algo,
+             cudaStream_t s) {
+    if (M == 0 || N == 0) return LT_OK;
+    if (algo == 0 || algo == 2) {
+        bool handled = false;
+        LT_TRY(gemm_3xtf32(A, lda, a_rows, B, ldb, transB, bias, relu, C, ldc, M, N, K, s, &handled));
+        if (handled) return LT_OK;
+        if (algo == 2) {
+            set_error("lt_gemm_f32: algo=2 (3xTF32 tensor cores) does not cover M=%d N=%d K=%d transB=%d", M, N, K,
+                      transB);
+            return LT_ERR_ARG;
+        }
+    }
+    dim3 grid((unsigned)ceil_div(N, GM_BN), (unsigned)ceil_div(M, GM_BM));
+    if (transB)
+        k_gemm_simt<true><<<grid, GM_THREADS, 0, s>>>(A, lda, a_rows, B, ldb, bias, relu, C, ldc, M, N, K);
+    else
+        k_gemm_simt<false><<<grid, GM_THREADS, 0, s>>>(A, lda, a_rows, B, ldb, bias, relu, C, ldc, M, N, K);
+    LT_LAUNCH_CHECK();
+    return LT_OK;
+}
+
+}  // namespace lt
+
+extern "C" int lt_gemm_f32(const float* A, int64_t lda, const int32_t* a_rows, const float* B, int64_t ldb,
+                           int transB, const float* bias, int relu, float* C, int64_t ldc, int32_t M, int32_t N,
+                           int32_t K, int algo, lt_stream_t stream) {
+    LT_CHECK_ARG(A && B && C && M >= 0 && N >= 0 && K >= 0 && lda >= K && ldc >= N, "lt_gemm_f32");
+    LT_CHECK_ARG(transB ? ldb >= K : ldb >= N, "lt_gemm_f32: ldb");
+    LT_CHECK_ARG(algo >= 0 && algo <= 2, "lt_gemm_f32: algo");
+    return lt::gemm_f32(A, lda, a_rows, B, ldb, transB, bias, relu, C, ldc, M, N, K, algo, (cudaStream_t)stream);
+}

@@ -1,0 +1,79 @@
+// Library plumbing: thread-local error message, device info, GCN forward composed from the kernels.
+#include "common.cuh"
+
+#include <string.h>
+
+namespace lt {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int num_sms() {
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+    }
+    return sms;
+}
+
+int gemm_f32(const float* A, int64_t lda, const int32_t* a_rows, const float* B, int64_t ldb, int transB,
+             const float* bias, int relu, float* C, int64_t ldc, int32_t M, int32_t N, int32_t K, int algo,
+             cudaStream_t s);
+int spmm_csr_f32(const int32_t* indptr, const int32_t* indices, const float* values, const int32_t* rows,
+                 int32_t n_rows, const float* B, int64_t ldb, int32_t d, const float* bias, int relu, float* C,
+                 int64_t ldc, cudaStream_t s);
+
+}  // namespace lt
+
+using namespace lt;
+
+extern "C" const char* lt_last_error(void) { return g_err; }
+extern "C" int lt_version(void) { return 100; }
+
+extern "C" int lt_device_info(int* sm_count_host, int* cc_major_host, int* cc_minor_host, int64_t* mem_bytes_host) {
+    int dev = 0;
+    LT_CUDA(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    LT_CUDA(cudaGetDeviceProperties(&prop, dev));
+    if (sm_count_host) *sm_count_host = prop.multiProcessorCount;
+    if (cc_major_host) *cc_major_host = prop.major;
+    if (cc_minor_host) *cc_minor_host = prop.minor;
+    if (mem_bytes_host) *mem_bytes_host = (int64_t)prop.totalGlobalMem;
+    // keep freed stream-ordered scratch in the pool instead of returning it to the driver at every sync
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        uint64_t thr = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    return LT_OK;
+}
+
+// GCN.forward (gcn/models.py:19-24), eval mode: Z = Â·(relu(Â·(X·W1) + b1)·W2) + b2
+extern "C" int lt_gcn_forward(const int32_t* indptr, const int32_t* indices, const float* values, int32_t n,
+                              const float* X, int64_t ldx, int32_t f, const float* W1, const float* b1,
+                              const float* W2, const float* b2, int32_t h, int32_t c, float* logits, int64_t ldz,
+                              lt_stream_t stream) {
+    LT_CHECK_ARG(indptr && indices && values && X && W1 && W2 && logits, "lt_gcn_forward: null pointer");
+    LT_CHECK_ARG(n > 0 && f > 0 && h > 0 && c > 0 && ldx >= f && ldz >= c, "lt_gcn_forward: sizes");
+    cudaStream_t s = (cudaStream_t)stream;
+    Scratch scratch(s);
+    float *P, *Rl, *Q;
+    const int64_t hp = (h + 3) / 4 * 4;   // padded leading dimension keeps the float4 SpMM path
+    LT_TRY(scratch.alloc(&P, (size_t)n * hp));
+    LT_TRY(scratch.alloc(&Rl, (size_t)n * hp));
+    LT_TRY(scratch.alloc(&Q, (size_t)n * c));
+    LT_TRY(gemm_f32(X, ldx, nullptr, W1, h, 0, nullptr, 0, P, hp, n, h, f, 0, s));            // layers.py:31
+    LT_TRY(spmm_csr_f32(indptr, indices, values, nullptr, n, P, hp, h, b1, 1, Rl, hp, s));     // :32-34 + relu
+    LT_TRY(gemm_f32(Rl, hp, nullptr, W2, c, 0, nullptr, 0, Q, c, n, c, h, 0, s));
+    LT_TRY(spmm_csr_f32(indptr, indices, values, nullptr, n, Q, c, c, b2, 0, logits, ldz, s));
+    return LT_OK;
+}

@@ -1,0 +1,112 @@
+// Device-wide exclusive prefix sum (reduce → scan of block sums → downsweep), recursive over
+// block sums.  Used by the CSR build, the frontier plan, the radix sort and the ranking kernels.
+#include "common.cuh"
+
+namespace lt {
+
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 16;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;  // 4096
+
+// Block-wide exclusive scan of one value per thread; returns the exclusive prefix and the block
+// total (in `total`).  All SCAN_THREADS threads must call.
+template <typename T>
+__device__ __forceinline__ T block_exclusive_scan(T v, T& total) {
+    __shared__ T warp_tot[SCAN_THREADS / 32];
+    __shared__ T blk_tot;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    T inc = warp_inclusive_scan(v);
+    if (lane == 31) warp_tot[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        T w = lane < SCAN_THREADS / 32 ? warp_tot[lane] : T(0);
+        T winc = warp_inclusive_scan(w);
+        if (lane < SCAN_THREADS / 32) warp_tot[lane] = winc - w;  // exclusive prefix of the warp
+        if (lane == SCAN_THREADS / 32 - 1) blk_tot = winc;
+    }
+    __syncthreads();
+    T res = warp_tot[warp] + inc - v;
+    total = blk_tot;
+    __syncthreads();  // shared arrays are reused by the next call
+    return res;
+}
+
+// the input is treated as having n_in valid elements; indices >= n_in read as 0
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_reduce(const TI* __restrict__ in, int64_t n_in,
+                                                             TO* __restrict__ block_sums) {
+    const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+    TO s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        int64_t i = base + k;
+        if (i < n_in) s += (TO)in[i];
+    }
+    TO total;
+    block_exclusive_scan<TO>(s, total);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+
+// out[i] = offsets[block] + exclusive prefix inside the tile, for i < n_out
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_down(const TI* in, int64_t n_in, TO* out,
+                                                           int64_t n_out,
+                                                           const TO* __restrict__ offsets) {
+    const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+    TO v[SCAN_ITEMS];
+    TO s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        int64_t i = base + k;
+        v[k] = (i < n_in) ? (TO)in[i] : TO(0);
+        s += v[k];
+    }
+    TO total;
+    TO pre = block_exclusive_scan<TO>(s, total);
+    pre += offsets ? offsets[blockIdx.x] : TO(0);
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        int64_t i = base + k;
+        if (i < n_out) out[i] = pre;
+        pre += v[k];
+    }
+}
+
+// Exclusive scan producing n_in+1 outputs (out[n_in] = total).  in may alias out when TI == TO
+// (every tile is fully read into registers before it is written, tiles do not overlap).
+template <typename TI, typename TO>
+static int scan_impl(const TI* in, TO* out, int64_t n_in, cudaStream_t s) {
+    const int64_t n_out = n_in + 1;
+    const int64_t blocks = ceil_div(n_out, SCAN_TILE);
+    if (blocks == 1) {
+        k_scan_down<TI, TO><<<1, SCAN_THREADS, 0, s>>>(in, n_in, out, n_out, nullptr);
+        LT_LAUNCH_CHECK();
+        return LT_OK;
+    }
+    Scratch scratch(s);
+    TO* sums = nullptr;
+    LT_TRY(scratch.alloc(&sums, (size_t)blocks + 1));
+    k_scan_reduce<TI, TO><<<(unsigned)blocks, SCAN_THREADS, 0, s>>>(in, n_in, sums);
+    LT_LAUNCH_CHECK();
+    LT_TRY((scan_impl<TO, TO>(sums, sums, blocks, s)));
+    k_scan_down<TI, TO><<<(unsigned)blocks, SCAN_THREADS, 0, s>>>(in, n_in, out, n_out, sums);
+    LT_LAUNCH_CHECK();
+    return LT_OK;
+}
+
+int exclusive_scan_i32(const int32_t* in, int32_t* out, int64_t n, cudaStream_t s) {
+    return scan_impl<int32_t, int32_t>(in, out, n, s);
+}
+int exclusive_scan_i64(const int64_t* in, int64_t* out, int64_t n, cudaStream_t s) {
+    return scan_impl<int64_t, int64_t>(in, out, n, s);
+}
+int exclusive_scan_i32_to_i64(const int32_t* in, int64_t* out, int64_t n, cudaStream_t s) {
+    return scan_impl<int32_t, int64_t>(in, out, n, s);
+}
+
+}  // namespace lt
+
+extern "C" int lt_exclusive_scan_i32(const int32_t* in, int32_t* out, int64_t n, lt_stream_t stream) {
+    LT_CHECK_ARG(n >= 0 && (in || n == 0) && out, "lt_exclusive_scan_i32");
+    return lt::exclusive_scan_i32(in, out, n, (cudaStream_t)stream);
+}

@@ -1,0 +1,389 @@
+"""Torch-tensor front end of the C ABI.  PyTorch is plumbing here (device memory, streams): every
+function validates its tensors, passes raw device pointers + the current CUDA stream to
+liblinkteller_b200.so and returns torch tensors that own the outputs."""
+from __future__ import annotations
+
+import ctypes as C
+import dataclasses
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+
+NORM_KINDS = {"FirstOrderGCN": 0, "AugNormAdj": 1}
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _chk(t: torch.Tensor, dtype, name: str, ndim=None):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise TypeError(f"{name}: expected a CUDA tensor")
+    if t.dtype != dtype:
+        raise TypeError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if ndim is not None and t.dim() != ndim:
+        raise ValueError(f"{name}: expected {ndim} dims, got {t.dim()}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name}: must be contiguous")
+    return t
+
+
+def _rowmajor(t: torch.Tensor, name: str):
+    """2-D float32 CUDA tensor with unit column stride; returns (tensor, leading dimension)."""
+    if not isinstance(t, torch.Tensor) or not t.is_cuda or t.dtype != torch.float32 or t.dim() != 2:
+        raise TypeError(f"{name}: expected a 2-D float32 CUDA tensor")
+    if t.stride(1) != 1 and t.shape[1] > 1:
+        t = t.contiguous()
+    ld = t.stride(0) if t.shape[0] > 1 else max(t.shape[1], 1)
+    if ld < t.shape[1]:
+        t = t.contiguous()
+        ld = t.shape[1]
+    return t, ld
+
+
+def device_info():
+    lib = _lib.load()
+    sm, ma, mi, mem = C.c_int(), C.c_int(), C.c_int(), C.c_int64()
+    _lib.check(lib.lt_device_info(C.byref(sm), C.byref(ma), C.byref(mi), C.byref(mem)), "lt_device_info")
+    return dict(sm_count=sm.value, cc=(ma.value, mi.value), mem_bytes=mem.value)
+
+
+@dataclasses.dataclass
+class DeviceCSR:
+    """CSR matrix resident in HBM: indptr int32[n+1], indices int32[nnz], values float32/float64."""
+    indptr: torch.Tensor
+    indices: torch.Tensor
+    values: torch.Tensor
+    n: int
+
+    @property
+    def nnz(self) -> int:
+        return int(self.indices.numel())
+
+    @classmethod
+    def from_scipy(cls, mat, device="cuda", value_dtype=None):
+        mat = mat.tocsr()
+        if not mat.has_canonical_format:
+            mat = mat.copy()
+            mat.sum_duplicates()
+        vd = value_dtype or (np.float32 if mat.data.dtype == np.float32 else np.float64)
+        return cls(torch.from_numpy(mat.indptr.astype(np.int32)).to(device),
+                   torch.from_numpy(mat.indices.astype(np.int32)).to(device),
+                   torch.from_numpy(mat.data.astype(vd)).to(device), int(mat.shape[0]))
+
+    def to_scipy(self):
+        import scipy.sparse as sp
+        return sp.csr_matrix((self.values.cpu().numpy(), self.indices.cpu().numpy(), self.indptr.cpu().numpy()),
+                             shape=(self.n, self.n))
+
+
+# ------------------------------------------------------------------------------------------ a1
+def csr_from_edges(edges: torch.Tensor, n: int, binarize: bool = False) -> DeviceCSR:
+    """graph_reader, utils/load.py:457-460: csr(ones,(r,c)) + its transpose, duplicates summed."""
+    lib = _lib.load()
+    _chk(edges, torch.int64, "edges", 2)
+    m = edges.shape[0]
+    dev = edges.device
+    indptr = torch.empty(n + 1, dtype=torch.int32, device=dev)
+    cap = max(2 * m, 1)
+    indices = torch.empty(cap, dtype=torch.int32, device=dev)
+    values = torch.empty(cap, dtype=torch.float32, device=dev)
+    nnz = C.c_int64()
+    _lib.check(lib.lt_csr_from_edges(_p(edges), m, n, int(binarize), _p(indptr), _p(indices), _p(values), cap,
+                                     C.byref(nnz), _stream()), "lt_csr_from_edges")
+    k = nnz.value
+    return DeviceCSR(indptr, indices[:k], values[:k], n)
+
+
+def coo_to_csr(row: torch.Tensor, col: torch.Tensor, values: torch.Tensor, n: int, check: bool = True) -> DeviceCSR:
+    """The torch COO `adj` (utils/load.py:552-559) → CSR; COO must be row-major sorted, no duplicates."""
+    lib = _lib.load()
+    _chk(row, torch.int64, "row", 1)
+    _chk(col, torch.int64, "col", 1)
+    nnz = row.numel()
+    indptr = torch.empty(n + 1, dtype=torch.int32, device=row.device)
+    indices = torch.empty(max(nnz, 1), dtype=torch.int32, device=row.device)
+    _lib.check(lib.lt_coo_to_csr(_p(row), _p(col), nnz, n, _p(indptr), _p(indices), _stream()), "lt_coo_to_csr")
+    indices = indices[:nnz]
+    if check:
+        ok = C.c_int()
+        _lib.check(lib.lt_csr_check(_p(indptr), _p(indices), n, nnz, C.byref(ok), _stream()), "lt_csr_check")
+        if not ok.value:
+            raise ValueError("adjacency COO tensor is not row-major sorted / duplicate-free; "
+                             "build it with linkteller_b200.adj.sparse_mx_to_torch_sparse_tensor")
+    return DeviceCSR(indptr, indices, values.contiguous(), n)
+
+
+# ------------------------------------------------------------------------------------------ a2
+def normalize_adj(adj: DeviceCSR, kind: str = "FirstOrderGCN") -> DeviceCSR:
+    """fetch_normalization(kind)(adj) + float32 cast (utils/load.py:562-578, 554), bit-exact.
+
+    Precision of the arithmetic follows the reference: float32 only for FirstOrderGCN on a float32
+    adjacency, float64 otherwise.  d^-1/2 is evaluated on the host by numpy exactly as upstream
+    (np.power(row_sum, -0.5); inf → 0) so that the values agree bit for bit."""
+    lib = _lib.load()
+    if kind not in NORM_KINDS:
+        raise NotImplementedError(f"normalisation {kind!r} is outside the hot-path scope")
+    k = NORM_KINDS[kind]
+    f32 = adj.values.dtype == torch.float32 and kind == "FirstOrderGCN"
+    vals = adj.values if f32 else adj.values.to(torch.float64)
+    vals = vals.contiguous()
+    prec = 0 if f32 else 1
+    n = adj.n
+    rs = torch.empty(n, dtype=vals.dtype, device=vals.device)
+    _lib.check(lib.lt_csr_row_sums(_p(adj.indptr), _p(vals), n, prec, _p(rs), _stream()), "lt_csr_row_sums")
+    rs_h = rs.cpu().numpy()
+    if kind == "AugNormAdj":
+        rs_h = rs_h + 1.0                                   # row sums of adj + sp.eye
+    with np.errstate(divide="ignore"):
+        d = np.power(rs_h, -0.5)                            # utils/load.py:565 / 575
+    d[np.isinf(d)] = 0.0
+    d_dev = torch.from_numpy(d).to(vals.device)
+    cap = adj.nnz + n
+    out_indptr = torch.empty(n + 1, dtype=torch.int32, device=vals.device)
+    out_indices = torch.empty(cap, dtype=torch.int32, device=vals.device)
+    out_values = torch.empty(cap, dtype=torch.float32, device=vals.device)
+    nnz = C.c_int64()
+    _lib.check(lib.lt_adj_normalize(_p(adj.indptr), _p(adj.indices), _p(vals), n, k, prec, _p(d_dev), _p(out_indptr),
+                                    _p(out_indices), _p(out_values), cap, C.byref(nnz), _stream()), "lt_adj_normalize")
+    m = nnz.value
+    return DeviceCSR(out_indptr, out_indices[:m], out_values[:m], n)
+
+
+# ------------------------------------------------------------------------------------------ a4/a5
+def gemm(a: torch.Tensor, b: torch.Tensor, bias: Optional[torch.Tensor] = None, relu: bool = False,
+         a_rows: Optional[torch.Tensor] = None, trans_b: bool = False, algo: int = 0) -> torch.Tensor:
+    lib = _lib.load()
+    a, lda = _rowmajor(a, "a")
+    b, ldb = _rowmajor(b, "b")
+    K = a.shape[1]
+    M = a.shape[0] if a_rows is None else a_rows.numel()
+    N = b.shape[0] if trans_b else b.shape[1]
+    if (b.shape[1] if trans_b else b.shape[0]) != K:
+        raise ValueError("gemm: inner dimensions differ")
+    if a_rows is not None:
+        _chk(a_rows, torch.int32, "a_rows", 1)
+    if bias is not None:
+        _chk(bias, torch.float32, "bias", 1)
+    out = torch.empty((M, N), dtype=torch.float32, device=a.device)
+    _lib.check(lib.lt_gemm_f32(_p(a), lda, _p(a_rows), _p(b), ldb, int(trans_b), _p(bias), int(relu), _p(out), N, M, N,
+                               K, algo, _stream()), "lt_gemm_f32")
+    return out
+
+
+def spmm(adj: DeviceCSR, b: torch.Tensor, bias: Optional[torch.Tensor] = None, relu: bool = False,
+         rows: Optional[torch.Tensor] = None) -> torch.Tensor:
+    lib = _lib.load()
+    b, ldb = _rowmajor(b, "b")
+    _chk(adj.values, torch.float32, "adj.values", 1)
+    if b.shape[0] != adj.n:
+        raise ValueError("spmm: dense operand must have n rows")
+    d = b.shape[1]
+    n_rows = adj.n if rows is None else rows.numel()
+    if rows is not None:
+        _chk(rows, torch.int32, "rows", 1)
+    if bias is not None:
+        _chk(bias, torch.float32, "bias", 1)
+    out = torch.empty((n_rows, d), dtype=torch.float32, device=b.device)
+    _lib.check(lib.lt_spmm_csr_f32(_p(adj.indptr), _p(adj.indices), _p(adj.values), _p(rows), n_rows, _p(b), ldb, d,
+                                   _p(bias), int(relu), _p(out), d, _stream()), "lt_spmm_csr_f32")
+    return out
+
+
+def gcn_forward(adj: DeviceCSR, x, w1, b1, w2, b2) -> torch.Tensor:
+    lib = _lib.load()
+    x, ldx = _rowmajor(x, "x")
+    w1 = _chk(w1, torch.float32, "w1", 2)
+    w2 = _chk(w2, torch.float32, "w2", 2)
+    n, f = x.shape
+    h, c = w2.shape
+    out = torch.empty((n, c), dtype=torch.float32, device=x.device)
+    _lib.check(lib.lt_gcn_forward(_p(adj.indptr), _p(adj.indices), _p(adj.values), n, _p(x), ldx, f, _p(w1), _p(b1),
+                                  _p(w2), _p(b2), h, c, _p(out), c, _stream()), "lt_gcn_forward")
+    return out
+
+
+# ------------------------------------------------------------------------------------------ a7/a8
+INFO_KEYS = ("frontier_rows", "incidences", "observer_entries", "records", "support_pairs", "frontier_bytes",
+             "frontier_row_nnz", "reserved")
+
+
+def attack_efficient(adj: DeviceCSR, x, w1, b1, w2, test_nodes: torch.Tensor, delta: float,
+                     lo: int = 0, hi: Optional[int] = None, out: Optional[torch.Tensor] = None,
+                     want_info: bool = False):
+    """Influence rows [hi-lo, T] for the perturbed nodes test_nodes[lo:hi] — the whole hot path of
+    one rank (plan + restricted precompute + frontier kernels) in one C call."""
+    lib = _lib.load()
+    x, ldx = _rowmajor(x, "x")
+    w1 = _chk(w1, torch.float32, "w1", 2)
+    w2 = _chk(w2, torch.float32, "w2", 2)
+    _chk(b1, torch.float32, "b1", 1)
+    _chk(test_nodes, torch.int32, "test_nodes", 1)
+    _chk(adj.values, torch.float32, "adj.values", 1)
+    T = test_nodes.numel()
+    hi = T if hi is None else hi
+    n, f = x.shape
+    h, c = w2.shape
+    if out is None:
+        out = torch.empty((hi - lo, T), dtype=torch.float32, device=x.device)
+    else:
+        _chk(out, torch.float32, "out", 2)
+    info = (C.c_int64 * 8)()
+    _lib.check(lib.lt_attack_efficient(_p(adj.indptr), _p(adj.indices), _p(adj.values), n, _p(x), ldx, f, _p(w1),
+                                       _p(b1), _p(w2), h, c, _p(test_nodes), T, lo, hi, float(delta), _p(out),
+                                       out.stride(0), info if want_info else None, _stream()), "lt_attack_efficient")
+    if want_info:
+        return out, dict(zip(INFO_KEYS, list(info)))
+    return out
+
+
+class Plan:
+    """Symbolic structure of one attack slice (lt_plan); owns device buffers until closed."""
+
+    def __init__(self, adj: DeviceCSR, test_nodes: torch.Tensor, lo: int = 0, hi: Optional[int] = None):
+        lib = _lib.load()
+        _chk(test_nodes, torch.int32, "test_nodes", 1)
+        _chk(adj.values, torch.float32, "adj.values", 1)
+        self.T = test_nodes.numel()
+        self.lo, self.hi = lo, self.T if hi is None else hi
+        self._h = C.c_void_p()
+        self._keep = (adj, test_nodes)
+        _lib.check(lib.lt_plan_create(_p(adj.indptr), _p(adj.indices), _p(adj.values), adj.n, _p(test_nodes), self.T,
+                                      self.lo, self.hi, _stream(), C.byref(self._h)), "lt_plan_create")
+
+    def info(self, h: int, c: int):
+        info = (C.c_int64 * 8)()
+        _lib.check(_lib.load().lt_plan_info(self._h, h, c, info, _stream()), "lt_plan_info")
+        return dict(zip(INFO_KEYS, list(info)))
+
+    def rows(self) -> torch.Tensor:
+        """Frontier rows R (node ids, ascending) as an int32 CUDA tensor (copy)."""
+        lib = _lib.load()
+        r = self.info(4, 1)["frontier_rows"]
+        out = torch.empty(r, dtype=torch.int32, device=self._keep[1].device)
+        _lib.check(lib.lt_plan_copy_rows(self._h, _p(out), _stream()), "lt_plan_copy_rows")
+        return out
+
+    def influence_rows(self, h_r: torch.Tensor, p: torch.Tensor, w2: torch.Tensor, delta: float,
+                       p_index: Optional[torch.Tensor] = None) -> torch.Tensor:
+        lib = _lib.load()
+        h_r, ldh = _rowmajor(h_r, "h_r")
+        p, ldp = _rowmajor(p, "p")
+        w2 = _chk(w2, torch.float32, "w2", 2)
+        h, c = w2.shape
+        out = torch.empty((self.hi - self.lo, self.T), dtype=torch.float32, device=p.device)
+        _lib.check(lib.lt_influence_rows(self._h, _p(h_r), ldh, _p(p), ldp, _p(p_index), _p(w2), h, c, float(delta),
+                                         _p(out), self.T, _stream()), "lt_influence_rows")
+        return out
+
+    def close(self):
+        if self._h:
+            _lib.load().lt_plan_destroy(self._h, _stream())
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ------------------------------------------------------------------------------------------ a6/a8/a9
+def n_pairs(T: int) -> int:
+    return T * (T - 1) // 2
+
+
+def pair_labels(adj_ori: DeviceCSR, test_nodes: torch.Tensor):
+    """_get_edge_sets_among_nodes (utils/load.py:304-326): uint8 label of every pair i<j (row-major,
+    sample order) = test_nodes[j] stored in row test_nodes[i] of adj_ori.  Returns (labels, n_pos)."""
+    lib = _lib.load()
+    _chk(test_nodes, torch.int32, "test_nodes", 1)
+    T = test_nodes.numel()
+    labels = torch.empty(max(n_pairs(T), 1), dtype=torch.uint8, device=test_nodes.device)
+    npos = C.c_int64()
+    _lib.check(lib.lt_pair_labels(_p(adj_ori.indptr), _p(adj_ori.indices), adj_ori.n, _p(test_nodes), T, _p(labels),
+                                  C.byref(npos), _stream()), "lt_pair_labels")
+    return labels[:n_pairs(T)], npos.value
+
+
+def pair_scores(influence: torch.Tensor) -> torch.Tensor:
+    """score(i<j) = influence[j][i] (attacker.py:233-245), float32 [T(T-1)/2] in pair order."""
+    lib = _lib.load()
+    influence, ldi = _rowmajor(influence, "influence")
+    T = influence.shape[0]
+    if influence.shape[1] != T:
+        raise ValueError("influence must be square [T,T]")
+    out = torch.empty(max(n_pairs(T), 1), dtype=torch.float32, device=influence.device)
+    _lib.check(lib.lt_pair_scores(_p(influence), ldi, T, _p(out), _stream()), "lt_pair_scores")
+    return out[:n_pairs(T)]
+
+
+def auc_ap(scores: torch.Tensor, labels: torch.Tensor):
+    """ROC-AUC and average precision with sklearn's tie semantics (attacker.py:382-386)."""
+    lib = _lib.load()
+    _chk(scores, torch.float32, "scores", 1)
+    _chk(labels, torch.uint8, "labels", 1)
+    if scores.numel() != labels.numel():
+        raise ValueError("scores and labels differ in length")
+    auc, ap = C.c_double(), C.c_double()
+    _lib.check(lib.lt_auc_ap(_p(scores), _p(labels), scores.numel(), C.byref(auc), C.byref(ap), _stream()),
+               "lt_auc_ap")
+    return auc.value, ap.value
+
+
+def topk_tp(scores: torch.Tensor, labels: torch.Tensor, n_pos):
+    """True positives among the global top-n_pos scores for every n_pos (attack_stats_all.py:108-116);
+    returns (tp_min, tp_max) lists over the possible tie-breaks at the cut."""
+    lib = _lib.load()
+    _chk(scores, torch.float32, "scores", 1)
+    _chk(labels, torch.uint8, "labels", 1)
+    q = len(n_pos)
+    arr = (C.c_int64 * q)(*[int(v) for v in n_pos])
+    lo, hi = (C.c_int64 * q)(), (C.c_int64 * q)()
+    _lib.check(lib.lt_topk_tp(_p(scores), _p(labels), scores.numel(), arr, q, lo, hi, _stream()), "lt_topk_tp")
+    return list(lo), list(hi)
+
+
+# ------------------------------------------------------------------------------------------ a10
+LSA2_TRANSFORMS = {"none": 0, "softmax": 1, "sigmoid": 2}
+
+
+def lsa2_corr(mat: torch.Tensor, test_nodes: torch.Tensor, transform: str = "none") -> torch.Tensor:
+    """baseline_attack (attacker.py:287-334): dist [T,T] float32, strict upper triangle filled."""
+    lib = _lib.load()
+    mat, ldm = _rowmajor(mat, "mat")
+    _chk(test_nodes, torch.int32, "test_nodes", 1)
+    T = test_nodes.numel()
+    if T and (int(test_nodes.min()) < 0 or int(test_nodes.max()) >= mat.shape[0]):
+        raise IndexError("test node outside the matrix")
+    dist = torch.empty((T, T), dtype=torch.float32, device=mat.device)
+    _lib.check(lib.lt_lsa2_corr(_p(mat), ldm, mat.shape[1], _p(test_nodes), T, LSA2_TRANSFORMS[transform], _p(dist), T,
+                                _stream()), "lt_lsa2_corr")
+    return dist
+
+
+# ------------------------------------------------------------------------------------------ primitives (tests)
+def exclusive_scan_i32(x: torch.Tensor) -> torch.Tensor:
+    lib = _lib.load()
+    _chk(x, torch.int32, "x", 1)
+    out = torch.empty(x.numel() + 1, dtype=torch.int32, device=x.device)
+    _lib.check(lib.lt_exclusive_scan_i32(_p(x), _p(out), x.numel(), _stream()), "lt_exclusive_scan_i32")
+    return out
+
+
+def radix_sort_pairs(keys: torch.Tensor, vals: Optional[torch.Tensor], begin_bit=0, end_bit=64):
+    """In-place stable sort; keys/vals are int64 tensors reinterpreted as uint64."""
+    lib = _lib.load()
+    _chk(keys, torch.int64, "keys", 1)
+    if vals is not None:
+        _chk(vals, torch.int64, "vals", 1)
+    _lib.check(lib.lt_radix_sort_pairs_u64(_p(keys), _p(vals), keys.numel(), begin_bit, end_bit, _stream()),
+               "lt_radix_sort_pairs_u64")
+    return keys, vals
