@@ -186,6 +186,17 @@ int lt_dp_lapgraph_select(const int32_t* indptr, const int32_t* indices, const d
                           const double* noise, int64_t n_keep, int32_t* out_indptr, int32_t* out_indices,
                           float* out_values, int64_t cap, int64_t* nnz_host, lt_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Phase timers (measurement only).  When enabled, every kernel family launched by
+ * the calls above is bracketed by CUDA events on the caller's stream.  lt_prof_report synchronises
+ * the device and writes "name count total_ms\n" lines (aggregated by name, launch order) into buf;
+ * returns LT_ERR_CAPACITY if buf is too small.  Disabled by default: no events are recorded.
+ * ------------------------------------------------------------------------------------------- */
+int64_t lt_launch_count(void); /* kernels launched by this library in this process so far */
+int lt_prof_enable(int on);
+int lt_prof_reset(void);
+int lt_prof_report(char* buf_host, int64_t cap);
+
 /* primitives exported for the unit tests */
 int lt_exclusive_scan_i32(const int32_t* in, int32_t* out /* n+1 */, int64_t n, lt_stream_t stream);
 int lt_radix_sort_pairs_u64(uint64_t* keys, uint64_t* vals /* nullable */, int64_t n, int begin_bit,

@@ -49,10 +49,14 @@ _SIGS = {
     "lt_lsa2_corr": [P, I64, I32, P, I32, INT, P, I64, P],
     "lt_dp_edgerand_apply": [P, P, P, I32, P, P, I64, P, P, P, I64, P, P],
     "lt_dp_lapgraph_select": [P, P, P, I32, P, I64, P, P, P, I64, P, P],
+    "lt_launch_count": [],
+    "lt_prof_enable": [INT],
+    "lt_prof_reset": [],
+    "lt_prof_report": [C.c_char_p, I64],
     "lt_exclusive_scan_i32": [P, P, I64, P],
     "lt_radix_sort_pairs_u64": [P, P, I64, INT, INT, P],
 }
-_RESTYPE = {"lt_last_error": C.c_char_p, "lt_plan_rows": P}
+_RESTYPE = {"lt_last_error": C.c_char_p, "lt_plan_rows": P, "lt_launch_count": I64}
 
 
 class LibraryMissing(RuntimeError):

@@ -14,6 +14,7 @@ namespace lt {
 
 // ---- error reporting: thread-local message, negative int codes across the C ABI ----
 void set_error(const char* fmt, ...);
+extern long long g_launches;
 
 #define LT_CUDA(expr)                                                                        \
     do {                                                                                     \
@@ -38,7 +39,13 @@ void set_error(const char* fmt, ...);
         }                                                         \
     } while (0)
 
-#define LT_LAUNCH_CHECK() LT_CUDA(cudaGetLastError())
+// every kernel launch in the library is followed by one LT_LAUNCH_CHECK: it also counts launches
+// (lt_launch_count) so that a bench can state how many of our kernels ran
+#define LT_LAUNCH_CHECK()              \
+    do {                               \
+        ++lt::g_launches;              \
+        LT_CUDA(cudaGetLastError());   \
+    } while (0)
 
 // ---- stream-ordered scratch memory (freed in reverse order by the destructor) ----
 struct Scratch {
@@ -70,6 +77,14 @@ struct Scratch {
 };
 
 int device_alloc(void** out, size_t bytes, cudaStream_t s);
+
+// ---- phase timers (lt_prof_*): CUDA events on the launching stream, only when enabled ----
+struct ProfScope {
+    int slot;
+    cudaStream_t stream;
+    ProfScope(const char* name, cudaStream_t s);
+    ~ProfScope();
+};
 int num_sms();
 
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }

@@ -470,6 +470,7 @@ int influence_rows(const lt_plan* p, const float* H_R, int64_t ldh, const float*
     const unsigned bl = (unsigned)ceil_div(E, F1_TILE_E);
     const float inv_delta = 1.0f / delta;
     for (int32_t c0 = 0; c0 < c; c0 += 128) {
+        ProfScope prof("frontier_dq", s);
         const int32_t cw = c - c0 < 128 ? c - c0 : 128;
         const int nc = (cw + 31) / 32;
         const size_t smem = ((size_t)F1_TILE_E * F1_ASTRIDE + (size_t)F1_HK * 32 * nc) * sizeof(float);
@@ -486,6 +487,7 @@ int influence_rows(const lt_plan* p, const float* H_R, int64_t ldh, const float*
 #undef LT_F1
         LT_LAUNCH_CHECK();
     }
+    ProfScope prof2("frontier_reduce", s);
 #define LT_F2(G_)                                                                                              \
     k_frontier_reduce<G_><<<(unsigned)ceil_div(M * G_, 256), 256, 0, s>>>(p->rec_key, p->rec_val, p->grp_off,  \
                                                                           p->n_groups, dq, c, out, ldo)
@@ -526,7 +528,11 @@ extern "C" int lt_plan_create(const int32_t* indptr, const int32_t* indices, con
     cudaStream_t s = (cudaStream_t)stream;
     lt_plan* p = new lt_plan();
     p->n = n; p->T = T; p->lo = lo; p->hi = hi; p->Ts = hi - lo;
-    int st = plan_build(p, indptr, indices, values, test_nodes, s);
+    int st;
+    {
+        ProfScope prof("plan", s);
+        st = plan_build(p, indptr, indices, values, test_nodes, s);
+    }
     if (st != LT_OK) { lt_plan_destroy(p, stream); return st; }
     *plan_host = p;
     return LT_OK;
@@ -589,21 +595,36 @@ extern "C" int lt_attack_efficient(const int32_t* indptr, const int32_t* indices
         st = scratch.alloc(&HR, (size_t)R * h);
         if (st == LT_OK) st = scratch.alloc(&Pt, (size_t)Ts * h);
         // P_v = X[v]·W1 for the slice (gathered rows)
-        if (st == LT_OK) st = gemm_f32(X, ldx, test_nodes + lo, W1, h, 0, nullptr, 0, Pt, h, Ts, h, f, 0, s);
+        if (st == LT_OK) {
+            ProfScope prof("gemm_pv", s);
+            st = gemm_f32(X, ldx, test_nodes + lo, W1, h, 0, nullptr, 0, Pt, h, Ts, h, f, 0, s);
+        }
         const bool aggregate_first = (f < h) && (f % 4 == 0) && (ldx % 4 == 0) && ((uintptr_t)X % 16 == 0);
         if (st == LT_OK) {
             if (aggregate_first) {
                 // H_R = (Â[R,:]·X)·W1 + b1 : gathers f floats per non-zero instead of h
                 float* AX = nullptr;
                 st = scratch.alloc(&AX, (size_t)R * f);
-                if (st == LT_OK) st = spmm_csr_f32(indptr, indices, values, plan->rows, R, X, ldx, f, nullptr, 0, AX, f, s);
-                if (st == LT_OK) st = gemm_f32(AX, f, nullptr, W1, h, 0, b1, 0, HR, h, R, h, f, 0, s);
+                if (st == LT_OK) {
+                    ProfScope prof("spmm_ax", s);
+                    st = spmm_csr_f32(indptr, indices, values, plan->rows, R, X, ldx, f, nullptr, 0, AX, f, s);
+                }
+                if (st == LT_OK) {
+                    ProfScope prof("gemm_h", s);
+                    st = gemm_f32(AX, f, nullptr, W1, h, 0, b1, 0, HR, h, R, h, f, 0, s);
+                }
             } else {
                 // H_R = Â[R,:]·(X·W1) + b1
                 float* Pfull = nullptr;
                 st = scratch.alloc(&Pfull, (size_t)n * h);
-                if (st == LT_OK) st = gemm_f32(X, ldx, nullptr, W1, h, 0, nullptr, 0, Pfull, h, n, h, f, 0, s);
-                if (st == LT_OK) st = spmm_csr_f32(indptr, indices, values, plan->rows, R, Pfull, h, h, b1, 0, HR, h, s);
+                if (st == LT_OK) {
+                    ProfScope prof("gemm_p", s);
+                    st = gemm_f32(X, ldx, nullptr, W1, h, 0, nullptr, 0, Pfull, h, n, h, f, 0, s);
+                }
+                if (st == LT_OK) {
+                    ProfScope prof("spmm_h", s);
+                    st = spmm_csr_f32(indptr, indices, values, plan->rows, R, Pfull, h, h, b1, 0, HR, h, s);
+                }
             }
         }
         if (st == LT_OK) st = influence_rows(plan, HR, h, Pt, h, nullptr, W2, h, c, delta, out, ldo, s);

@@ -6,12 +6,34 @@
 namespace lt {
 
 static thread_local char g_err[1024] = "";
+long long g_launches = 0;
 
 void set_error(const char* fmt, ...) {
     va_list ap;
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
+}
+
+// ---- phase timers ----
+namespace {
+struct ProfRec { const char* name; cudaEvent_t a, b; };
+constexpr int PROF_MAX = 4096;
+ProfRec g_prof[PROF_MAX];
+int g_prof_n = 0;
+bool g_prof_on = false;
+}  // namespace
+
+ProfScope::ProfScope(const char* name, cudaStream_t s) : slot(-1), stream(s) {
+    if (!g_prof_on || g_prof_n >= PROF_MAX) return;
+    ProfRec& r = g_prof[g_prof_n];
+    if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
+    r.name = name;
+    slot = g_prof_n++;
+    cudaEventRecord(r.a, s);
+}
+ProfScope::~ProfScope() {
+    if (slot >= 0) cudaEventRecord(g_prof[slot].b, stream);
 }
 
 int num_sms() {
@@ -53,6 +75,42 @@ extern "C" int lt_device_info(int* sm_count_host, int* cc_major_host, int* cc_mi
     if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
         uint64_t thr = UINT64_MAX;
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    return LT_OK;
+}
+
+extern "C" int64_t lt_launch_count(void) { return (int64_t)g_launches; }
+extern "C" int lt_prof_enable(int on) { g_prof_on = on != 0; return LT_OK; }
+extern "C" int lt_prof_reset(void) {
+    for (int i = 0; i < g_prof_n; ++i) { cudaEventDestroy(g_prof[i].a); cudaEventDestroy(g_prof[i].b); }
+    g_prof_n = 0;
+    return LT_OK;
+}
+extern "C" int lt_prof_report(char* buf_host, int64_t cap) {
+    LT_CHECK_ARG(buf_host && cap > 0, "lt_prof_report");
+    LT_CUDA(cudaDeviceSynchronize());
+    const char* names[256];
+    int counts[256];
+    double total[256];
+    int nn = 0;
+    for (int i = 0; i < g_prof_n; ++i) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, g_prof[i].a, g_prof[i].b) != cudaSuccess) continue;
+        int k = 0;
+        while (k < nn && strcmp(names[k], g_prof[i].name) != 0) ++k;
+        if (k == nn) {
+            if (nn == 256) continue;
+            names[nn] = g_prof[i].name; counts[nn] = 0; total[nn] = 0.0; ++nn;
+        }
+        counts[k] += 1;
+        total[k] += ms;
+    }
+    int64_t off = 0;
+    buf_host[0] = 0;
+    for (int k = 0; k < nn; ++k) {
+        int w = snprintf(buf_host + off, (size_t)(cap - off), "%s %d %.6f\n", names[k], counts[k], total[k]);
+        if (w < 0 || off + w >= cap) { set_error("lt_prof_report: buffer too small"); return LT_ERR_CAPACITY; }
+        off += w;
     }
     return LT_OK;
 }

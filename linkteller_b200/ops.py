@@ -55,6 +55,39 @@ def device_info():
     return dict(sm_count=sm.value, cc=(ma.value, mi.value), mem_bytes=mem.value)
 
 
+def launch_count() -> int:
+    """Kernels launched by liblinkteller_b200 in this process so far."""
+    return int(_lib.load().lt_launch_count())
+
+
+class profile:
+    """Context manager around the library's phase timers: `with ops.profile() as p: ...; p.report()`
+    → {phase: (launch groups, total ms)} measured with CUDA events on the launching stream."""
+
+    def __enter__(self):
+        lib = _lib.load()
+        lib.lt_prof_reset()
+        lib.lt_prof_enable(1)
+        self._rep = None
+        return self
+
+    def __exit__(self, *exc):
+        lib = _lib.load()
+        lib.lt_prof_enable(0)
+        buf = C.create_string_buffer(1 << 16)
+        _lib.check(lib.lt_prof_report(buf, len(buf)), "lt_prof_report")
+        rep = {}
+        for line in buf.value.decode().splitlines():
+            name, cnt, ms = line.split()
+            rep[name] = (int(cnt), float(ms))
+        self._rep = rep
+        lib.lt_prof_reset()
+        return False
+
+    def report(self):
+        return self._rep
+
+
 @dataclasses.dataclass
 class DeviceCSR:
     """CSR matrix resident in HBM: indptr int32[n+1], indices int32[nnz], values float32/float64."""

@@ -417,3 +417,76 @@ def lapgraph(indptr, indices, data, n, epsilon, noise_seed):
     key = np.unique(np.concatenate([r * n + c, c * n + r]))
     ip, ix, dv = coo_to_csr(key // n, key % n, np.ones(len(key), dtype=np.int32), n)
     return ip, ix, dv, n_keep
+
+
+# --------------------------------------------------------------------------------------------
+# CPU timing of the reference's per-row work (bench.py cpu_baseline / --impl reference only)
+# --------------------------------------------------------------------------------------------
+
+def time_reference_rows(X, coo, weights, n, test_nodes, delta, n_rows, slice_div=1, threads=None):
+    """Seconds the reference's loop body (attacker.py:220-229 → 100-108 → gcn/models.py:19-24 →
+    gcn/layers.py:30-36) takes for `n_rows` influence rows, float32, torch CPU ops exactly as the
+    reference issues them.  Returns (seconds_per_row, description).
+
+    slice_div == 1: the rows are evaluated in full (influence_matrix above) and timed.
+    slice_div  > 1: for graphs where ONE row costs minutes on a CPU (config C5: ~1e8 non-zeros x
+      256 columns per sparse product), every dense op of the row is still executed and timed in
+      full, but the two torch.spmm calls of a forward run on the first 1/slice_div of Â's rows (a
+      contiguous COO slice) and their time is scaled by nnz(Â)/nnz(slice) — torch's COO spmm is a
+      single pass over the non-zeros, so the cost is linear in nnz.  The result is an extrapolated
+      timing, labelled as such by the caller; no values are produced in this mode.
+    """
+    import time
+    if threads:
+        torch.set_num_threads(threads)
+    row, col, val = coo
+    tn = np.asarray(test_nodes)
+    if slice_div <= 1:
+        t0 = time.perf_counter()
+        influence_matrix(X, coo, weights, n, tn, delta, dtype=torch.float32, rows=range(n_rows))
+        dt = (time.perf_counter() - t0) / n_rows
+        return dt, f"{n_rows} full rows (2 GCN forwards + {len(tn)} norms each), reference ops on torch CPU"
+    x = torch.from_numpy(np.asarray(X))
+    w1, b1, w2, b2 = [torch.from_numpy(np.asarray(a)) for a in weights]
+    n_s = max(1, n // slice_div)
+    cut = int(np.searchsorted(np.asarray(row), n_s))          # COO is row-major sorted
+    adj_s = _sparse(np.asarray(row[:cut]), np.asarray(col[:cut]), np.asarray(val[:cut]), n, torch.float32)
+    scale = len(row) / max(cut, 1)
+    sel = torch.from_numpy(tn.astype(np.int64))
+    tm = time.perf_counter
+    t_dense = t_sparse = 0.0
+    with torch.no_grad():
+        for i in range(n_rows):
+            v = int(tn[i])
+            t0 = tm()
+            pert = torch.zeros_like(x)                         # attacker.py:101-103
+            pert[v] = x[v] * delta
+            xp = x + pert
+            t_dense += tm() - t0
+            outs = []
+            for feats in (xp, x):                              # attacker.py:105-106: two forwards
+                t0 = tm()
+                sup = torch.mm(feats, w1)                      # layers.py:31
+                t_dense += tm() - t0
+                t0 = tm()
+                hs = torch.spmm(adj_s, sup)                    # layers.py:32 (sliced, extrapolated)
+                t_sparse += tm() - t0
+                t0 = tm()
+                hfull = torch.relu(sup + b1)                   # same-size stand-in for (Â·sup + b1), relu
+                sup2 = torch.mm(hfull, w2)
+                t_dense += tm() - t0
+                t0 = tm()
+                zs = torch.spmm(adj_s, sup2)
+                t_sparse += tm() - t0
+                t0 = tm()
+                outs.append(sup2 + b2)                         # [n,c] output of the forward
+                t_dense += tm() - t0
+                del hs, zs
+            t0 = tm()
+            grad = (outs[0] - outs[1]) / delta
+            for j in range(len(tn)):                           # attacker.py:224-229 (T .item() calls)
+                grad[sel[j]].norm().item()
+            t_dense += tm() - t0
+    per_row = (t_dense + t_sparse * scale) / n_rows
+    return per_row, (f"{n_rows} rows; dense ops in full, torch.spmm on the first 1/{slice_div} of Â's rows "
+                     f"({cut} of {len(row)} non-zeros) scaled by {scale:.2f} (extrapolated)")
