@@ -161,6 +161,12 @@ int lt_auc_ap(const float* scores, const uint8_t* labels, int64_t n_pairs, doubl
 int lt_topk_tp(const float* scores, const uint8_t* labels, int64_t n_pairs, const int64_t* n_pos_host,
                int32_t n_queries, int64_t* tp_min_host, int64_t* tp_max_host, lt_stream_t stream);
 
+/* a9  the curves compute_and_save stores (attacker.py:382-385 → sklearn _binary_clf_curve): one point
+ *     per distinct score in descending order — threshold, cumulative true and false positives.
+ *     cap == 0 queries the number of points (returned in *n_points_host).  Synchronises. */
+int lt_rank_curve(const float* scores, const uint8_t* labels, int64_t n_pairs, float* thresholds, int64_t* tps,
+                  int64_t* fps, int64_t cap, int64_t* n_points_host, lt_stream_t stream);
+
 /* a10 baseline_attack (LSA2-post / LSA2-attr), attacker.py:287-334: centred cosine similarity of
  *     the rows M[test_nodes[i], :d] after transform (0 none, 1 softmax, 2 sigmoid); dist [T,T]
  *     float32, upper triangle (i<j) filled, rest 0. */
@@ -174,16 +180,17 @@ int lt_lsa2_corr(const float* M, int64_t ldm, int32_t d, const int32_t* test_nod
  *     hits: int64 [n_hits] cell ids r*n+c with r<c, ascending; coin: uint8 [n_hits] (1 = add).
  *     Output values float64, capacity nnz+2·n_hits is always enough.  Synchronises.
  * a12 perturb_adj_continuous (Lapgraph), worker.py:281-335: noise is the host-drawn Laplace
- *     matrix (float64 [n,n], row-major); the device adds tril(A,-1), selects the exact top-n_keep
- *     cells of the strict lower triangle and rebuilds the symmetric binary CSR (int32 ones, as
- *     float32 here).  Capacity 2·n_keep.  Synchronises.
+ *     matrix (float64 [n,n], row-major); the device adds tril(A,-1) into it (worker.py:298), selects
+ *     the exact top-n_keep cells of the strict lower triangle (ties at the cut: lowest row-major
+ *     cell first) and rebuilds the symmetric binary CSR (int32 ones upstream, float32 here).
+ *     Capacity 2·n_keep.  Synchronises.
  * ------------------------------------------------------------------------------------------- */
 int lt_dp_edgerand_apply(const int32_t* indptr, const int32_t* indices, const double* values, int32_t n,
                          const int64_t* hits, const uint8_t* coin, int64_t n_hits, int32_t* out_indptr,
                          int32_t* out_indices, double* out_values, int64_t cap, int64_t* nnz_host,
                          lt_stream_t stream);
 int lt_dp_lapgraph_select(const int32_t* indptr, const int32_t* indices, const double* values, int32_t n,
-                          const double* noise, int64_t n_keep, int32_t* out_indptr, int32_t* out_indices,
+                          double* noise /* consumed: tril(A,-1) is added in place */, int64_t n_keep, int32_t* out_indptr, int32_t* out_indices,
                           float* out_values, int64_t cap, int64_t* nnz_host, lt_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------

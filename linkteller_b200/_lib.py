@@ -46,6 +46,7 @@ _SIGS = {
     "lt_pair_scores": [P, I64, I32, P, P],
     "lt_auc_ap": [P, P, I64, P, P, P],
     "lt_topk_tp": [P, P, I64, P, I32, P, P, P],
+    "lt_rank_curve": [P, P, I64, P, P, P, I64, P, P],
     "lt_lsa2_corr": [P, I64, I32, P, I32, INT, P, I64, P],
     "lt_dp_edgerand_apply": [P, P, P, I32, P, P, I64, P, P, P, I64, P, P],
     "lt_dp_lapgraph_select": [P, P, P, I32, P, I64, P, P, P, I64, P, P],

@@ -178,12 +178,11 @@ static int normalize_impl(const int32_t* indptr, const int32_t* indices, const T
 
 using namespace lt;
 
-extern "C" int lt_csr_from_edges(const int64_t* edges, int64_t m, int32_t n, int binarize, int32_t* indptr,
-                                 int32_t* indices, float* values, int64_t cap, int64_t* nnz_host,
-                                 lt_stream_t stream) {
+namespace lt {
+int csr_from_edges(const int64_t* edges, int64_t m, int32_t n, int binarize, int32_t* indptr, int32_t* indices,
+                   float* values, int64_t cap, int64_t* nnz_host, cudaStream_t s) {
     LT_CHECK_ARG((edges || m == 0) && indptr && indices && values && nnz_host && m >= 0 && n > 0, "lt_csr_from_edges");
     LT_CHECK_ARG(2 * m < ((int64_t)1 << 31), "lt_csr_from_edges: 2m must be < 2^31");
-    cudaStream_t s = (cudaStream_t)stream;
     const int64_t nk = 2 * m;
     if (nk == 0) {
         k_fill_i32<<<(unsigned)ceil_div(n + 1, 256), 256, 0, s>>>(indptr, n + 1, 0);
@@ -221,6 +220,13 @@ extern "C" int lt_csr_from_edges(const int64_t* edges, int64_t m, int32_t n, int
     k_run_values<<<(unsigned)ceil_div(nnz, 256), 256, 0, s>>>(starts, nnz, nk, binarize, values);
     LT_LAUNCH_CHECK();
     return LT_OK;
+}
+}  // namespace lt
+
+extern "C" int lt_csr_from_edges(const int64_t* edges, int64_t m, int32_t n, int binarize, int32_t* indptr,
+                                 int32_t* indices, float* values, int64_t cap, int64_t* nnz_host,
+                                 lt_stream_t stream) {
+    return lt::csr_from_edges(edges, m, n, binarize, indptr, indices, values, cap, nnz_host, (cudaStream_t)stream);
 }
 
 extern "C" int lt_coo_to_csr(const int64_t* row, const int64_t* col, int64_t nnz, int32_t n, int32_t* indptr,

@@ -49,8 +49,10 @@ struct lt_plan {
     uint64_t* rec_val = nullptr;  // [M] (e<<32 | float bits of w)
     int32_t* grp_off = nullptr;   // [M+1] start of every (j,i) group; first n_groups+1 entries valid
     int32_t* n_groups = nullptr;  // device scalar
+    int32_t* big = nullptr;       // [M / F2_BIG + 1] groups with more than F2_BIG records
+    int32_t* n_big = nullptr;     // device scalar
     int32_t n_groups_host = -1;
-    void* owned[16];
+    void* owned[24];
     int n_owned = 0;
 };
 
@@ -104,29 +106,28 @@ __global__ void k_compact_rows(const int32_t* __restrict__ flag, const int32_t* 
     }
 }
 
-// one warp per slice row j: S entries.  a_e = Â[r,v] looked up in row r (the value the reference's
-// spmm multiplies P'[v] with); a missing entry means Â's pattern is not symmetric.
+// one thread per incidence e: owner row j (binary search in s_indptr), frontier row r, and
+// a_e = Â[r,v] looked up in row r (the value the reference's spmm multiplies P'[v] with; a missing
+// entry means Â's pattern is not symmetric).  Thread-per-incidence keeps hub test nodes from
+// serialising thousands of binary searches in one warp.
 __global__ void k_fill_S(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
                          const float* __restrict__ values, const int32_t* __restrict__ test_nodes, int32_t lo,
-                         int32_t Ts, const int32_t* __restrict__ rmap, const int32_t* __restrict__ s_indptr,
-                         int32_t* __restrict__ s_j, int32_t* __restrict__ s_rho, float* __restrict__ s_a,
-                         int* __restrict__ err) {
-    const int lane = threadIdx.x & 31;
-    const int64_t j = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (j >= Ts) return;
+                         int32_t Ts, int64_t E, const int32_t* __restrict__ rmap,
+                         const int32_t* __restrict__ s_indptr, int32_t* __restrict__ s_j,
+                         int32_t* __restrict__ s_rho, float* __restrict__ s_a, int* __restrict__ err) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    const int32_t j = (int32_t)upper_bound(s_indptr, 0, (int64_t)Ts + 1, (int32_t)e) - 1;
     const int32_t v = test_nodes[lo + j];
-    const int32_t beg = indptr[v], len = indptr[v + 1] - beg, dst = s_indptr[j];
-    for (int32_t k = lane; k < len; k += 32) {
-        const int32_t r = indices[beg + k];
-        const int32_t rb = indptr[r], re = indptr[r + 1];
-        const int64_t p = lower_bound(indices, (int64_t)rb, (int64_t)re, v);
-        float a;
-        if (p < re && indices[p] == v) a = values[p];
-        else { a = 0.f; atomicOr(err, 4); }
-        s_j[dst + k] = (int32_t)j;
-        s_rho[dst + k] = rmap[r];
-        s_a[dst + k] = a;
-    }
+    const int32_t r = indices[indptr[v] + ((int32_t)e - s_indptr[j])];
+    const int32_t rb = indptr[r], re = indptr[r + 1];
+    const int64_t p = lower_bound(indices, (int64_t)rb, (int64_t)re, v);
+    float a;
+    if (p < re && indices[p] == v) a = values[p];
+    else { a = 0.f; atomicOr(err, 4); }
+    s_j[e] = j;
+    s_rho[e] = rmap[r];
+    s_a[e] = a;
 }
 
 // observers: one warp per test node i (all T).  MODE 0 counts per frontier row, MODE 1 fills.
@@ -290,7 +291,34 @@ k_frontier_dq(const int32_t* __restrict__ s_j, const int32_t* __restrict__ s_rho
 }
 
 // ------------------------------------------------------------------------------------ F2
-// G lanes per output pair.  out[j,i] = sqrt(Σ_col (Σ_k w_k·ΔQ[e_k,col])²)
+// out[j,i] = sqrt(Σ_col (Σ_k w_k·ΔQ[e_k,col])²) per output pair (group of records).
+// Small groups: G lanes per group, lanes ↔ columns, record loop unrolled for memory-level
+// parallelism.  Groups above F2_BIG records (the (v,v) pair of a hub test node has deg(v)+1
+// records) are listed in the plan and reduced by a whole CTA each, so no warp walks thousands of
+// records alone.  Summation order is fixed per group ⇒ results are deterministic.
+constexpr int F2_BIG = 64;
+constexpr int F2_BIG_WARPS = 32;   // 1024-thread CTA per big group
+
+__device__ __forceinline__ float f2_column(const uint64_t* __restrict__ val, const float* __restrict__ dq, int32_t c,
+                                           int col, int32_t m0, int32_t m1) {
+    float z0 = 0.f, z1 = 0.f, z2 = 0.f, z3 = 0.f;
+    int32_t m = m0;
+    for (; m + 4 <= m1; m += 4) {
+        const uint64_t v0 = val[m], v1 = val[m + 1], v2 = val[m + 2], v3 = val[m + 3];
+        const float d0 = dq[(int64_t)(v0 >> 32) * c + col], d1 = dq[(int64_t)(v1 >> 32) * c + col];
+        const float d2 = dq[(int64_t)(v2 >> 32) * c + col], d3 = dq[(int64_t)(v3 >> 32) * c + col];
+        z0 = fmaf(__uint_as_float((uint32_t)v0), d0, z0);
+        z1 = fmaf(__uint_as_float((uint32_t)v1), d1, z1);
+        z2 = fmaf(__uint_as_float((uint32_t)v2), d2, z2);
+        z3 = fmaf(__uint_as_float((uint32_t)v3), d3, z3);
+    }
+    for (; m < m1; ++m) {
+        const uint64_t v = val[m];
+        z0 = fmaf(__uint_as_float((uint32_t)v), dq[(int64_t)(v >> 32) * c + col], z0);
+    }
+    return (z0 + z1) + (z2 + z3);
+}
+
 template <int G>
 __global__ void __launch_bounds__(256)
 k_frontier_reduce(const uint64_t* __restrict__ key, const uint64_t* __restrict__ val,
@@ -299,19 +327,19 @@ k_frontier_reduce(const uint64_t* __restrict__ key, const uint64_t* __restrict__
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t g = t / G;
     const int sub = (int)(t % G);
-    const bool valid = g < *n_groups;
+    bool valid = g < *n_groups;
     float ss = 0.f;
     uint64_t k0 = 0;
     if (valid) {
         const int32_t m0 = grp_off[g], m1 = grp_off[g + 1];
-        k0 = key[m0];
-        for (int col = sub; col < c; col += G) {
-            float z = 0.f;
-            for (int32_t m = m0; m < m1; ++m) {
-                const uint64_t v = val[m];
-                z = fmaf(__uint_as_float((uint32_t)v), dq[(int64_t)(v >> 32) * c + col], z);
+        if (m1 - m0 > F2_BIG) {
+            valid = false;            // k_frontier_reduce_big owns this group
+        } else {
+            k0 = key[m0];
+            for (int col = sub; col < c; col += G) {
+                const float z = f2_column(val, dq, c, col, m0, m1);
+                ss = fmaf(z, z, ss);
             }
-            ss = fmaf(z, z, ss);
         }
     }
 #pragma unroll
@@ -319,8 +347,53 @@ k_frontier_reduce(const uint64_t* __restrict__ key, const uint64_t* __restrict__
     if (valid && sub == 0) out[(int64_t)(k0 >> 32) * ldo + (int64_t)(k0 & 0xffffffffu)] = sqrtf(ss);
 }
 
+// thread per group: append the groups with more than F2_BIG records to big[]
+__global__ void k_big_groups(const int32_t* __restrict__ grp_off, const int32_t* __restrict__ n_groups,
+                             int32_t* __restrict__ big, int32_t* __restrict__ n_big) {
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= *n_groups) return;
+    if (grp_off[g + 1] - grp_off[g] > F2_BIG) big[atomicAdd(n_big, 1)] = (int32_t)g;
+}
+
+// one CTA (32 warps) per big group: warp w reduces the w-th contiguous chunk of the records
+// (lanes ↔ columns), partial sums meet in shared memory and are added in warp order.
+__global__ void __launch_bounds__(32 * F2_BIG_WARPS)
+k_frontier_reduce_big(const uint64_t* __restrict__ key, const uint64_t* __restrict__ val,
+                      const int32_t* __restrict__ grp_off, const int32_t* __restrict__ big,
+                      const int32_t* __restrict__ n_big, const float* __restrict__ dq, int32_t c,
+                      float* __restrict__ out, int64_t ldo) {
+    __shared__ float part[F2_BIG_WARPS][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int32_t b = blockIdx.x; b < *n_big; b += gridDim.x) {
+        const int32_t g = big[b];
+        const int32_t m0 = grp_off[g], m1 = grp_off[g + 1];
+        const int32_t chunk = (m1 - m0 + F2_BIG_WARPS - 1) / F2_BIG_WARPS;
+        const int32_t a0 = min(m1, m0 + warp * chunk), a1 = min(m1, a0 + chunk);
+        float ss = 0.f;   // meaningful in warp 0 only
+        for (int c0 = 0; c0 < c; c0 += 32) {
+            const int col = c0 + lane;
+            part[warp][lane] = col < c ? f2_column(val, dq, c, col, a0, a1) : 0.f;
+            __syncthreads();
+            if (warp == 0) {
+                float z = 0.f;
+#pragma unroll
+                for (int w = 0; w < F2_BIG_WARPS; ++w) z += part[w][lane];
+                ss = fmaf(z, z, ss);
+            }
+            __syncthreads();
+        }
+        if (warp == 0) {
+            ss = warp_sum(ss);
+            if (lane == 0) {
+                const uint64_t k0 = key[m0];
+                out[(int64_t)(k0 >> 32) * ldo + (int64_t)(k0 & 0xffffffffu)] = sqrtf(ss);
+            }
+        }
+    }
+}
+
 static int plan_own(lt_plan* p, void* ptr) {
-    if (p->n_owned >= 16) { set_error("plan: too many buffers"); return LT_ERR_INTERNAL; }
+    if (p->n_owned >= 24) { set_error("plan: too many buffers"); return LT_ERR_INTERNAL; }
     p->owned[p->n_owned++] = ptr;
     return LT_OK;
 }
@@ -386,9 +459,11 @@ static int plan_build(lt_plan* p, const int32_t* indptr, const int32_t* indices,
     LT_TRY(plan_alloc(p, &p->s_j, (size_t)E, s));
     LT_TRY(plan_alloc(p, &p->s_rho, (size_t)E, s));
     LT_TRY(plan_alloc(p, &p->s_a, (size_t)E, s));
-    k_fill_S<<<(unsigned)ceil_div((int64_t)Ts * 32, 256), 256, 0, s>>>(indptr, indices, values, test_nodes, lo, Ts, rmap,
-                                                                    p->s_indptr, p->s_j, p->s_rho, p->s_a, err);
-    LT_LAUNCH_CHECK();
+    if (E) {
+        k_fill_S<<<(unsigned)ceil_div(E, 256), 256, 0, s>>>(indptr, indices, values, test_nodes, lo, Ts, E, rmap,
+                                                            p->s_indptr, p->s_j, p->s_rho, p->s_a, err);
+        LT_LAUNCH_CHECK();
+    }
 
     // observers
     int32_t* cursor;
@@ -436,7 +511,10 @@ static int plan_build(lt_plan* p, const int32_t* indptr, const int32_t* indices,
     LT_TRY(plan_alloc(p, &p->rec_val, (size_t)M, s));
     LT_TRY(plan_alloc(p, &p->grp_off, (size_t)M + 2, s));
     LT_TRY(plan_alloc(p, &p->n_groups, 1, s));
+    LT_TRY(plan_alloc(p, &p->big, (size_t)(M / F2_BIG + 1), s));
+    LT_TRY(plan_alloc(p, &p->n_big, 1, s));
     LT_CUDA(cudaMemsetAsync(p->n_groups, 0, 4, s));
+    LT_CUDA(cudaMemsetAsync(p->n_big, 0, 4, s));
     if (M) {
         k_expand<<<(unsigned)ceil_div(E * 32, 256), 256, 0, s>>>(p->s_j, p->s_rho, E, p->b_indptr, p->b_i, p->b_w,
                                                                rec_off, p->rec_key, p->rec_val);
@@ -449,6 +527,8 @@ static int plan_build(lt_plan* p, const int32_t* indptr, const int32_t* indices,
         LT_LAUNCH_CHECK();
         LT_TRY(exclusive_scan_i32(head, head, M, s));
         k_group_offsets<<<(unsigned)ceil_div(M + 1, 256), 256, 0, s>>>(head, M, p->grp_off, p->n_groups);
+        LT_LAUNCH_CHECK();
+        k_big_groups<<<(unsigned)ceil_div(M, 256), 256, 0, s>>>(p->grp_off, p->n_groups, p->big, p->n_big);
         LT_LAUNCH_CHECK();
     }
     return LT_OK;
@@ -499,6 +579,11 @@ int influence_rows(const lt_plan* p, const float* H_R, int64_t ldh, const float*
     else LT_F2(32);
 #undef LT_F2
     LT_LAUNCH_CHECK();
+    if (M > F2_BIG) {
+        k_frontier_reduce_big<<<(unsigned)num_sms() * 2, 32 * F2_BIG_WARPS, 0, s>>>(p->rec_key, p->rec_val, p->grp_off, p->big, p->n_big,
+                                                                     dq, c, out, ldo);
+        LT_LAUNCH_CHECK();
+    }
     return LT_OK;
 }
 

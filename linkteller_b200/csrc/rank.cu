@@ -175,7 +175,24 @@ __global__ void k_topk_tp(const int32_t* __restrict__ gid, const int32_t* __rest
     tp_max[q] = tp_above + (need < tie_pos ? need : tie_pos);
 }
 
+// one thread per tie group: the curve point after consuming the group (sklearn's _binary_clf_curve:
+// one threshold per distinct score, descending) — threshold, cumulative TP and FP
+__global__ void k_rank_curve(const uint64_t* __restrict__ keys, const int32_t* __restrict__ gstart, int32_t G,
+                             const int32_t* __restrict__ tp_excl, float* __restrict__ thr, int64_t* __restrict__ tps,
+                             int64_t* __restrict__ fps) {
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= G) return;
+    const int64_t s = gstart[g], e = gstart[g + 1];
+    uint32_t u = ~(uint32_t)(keys[s] >> 32);                       // undo desc_key
+    u = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+    thr[g] = __uint_as_float(u);
+    const int64_t tp = tp_excl[e];
+    tps[g] = tp;
+    fps[g] = e - tp;
+}
+
 struct Ranking {
+    uint64_t* keys = nullptr;
     int32_t *gid = nullptr, *gstart = nullptr, *tp_excl = nullptr;
     int32_t G = 0;
 };
@@ -188,6 +205,7 @@ static int build_ranking(Scratch& scratch, const float* scores, const uint8_t* l
     int32_t* lab;
     int* err;
     LT_TRY(scratch.alloc(&keys, (size_t)n));
+    rk->keys = keys;
     LT_TRY(scratch.alloc(&rk->gid, (size_t)n + 1));
     LT_TRY(scratch.alloc(&lab, (size_t)n + 1));
     LT_TRY(scratch.alloc(&rk->gstart, (size_t)n + 2));
@@ -302,5 +320,24 @@ extern "C" int lt_topk_tp(const float* scores, const uint8_t* labels, int64_t n_
     LT_CUDA(cudaMemcpyAsync(tp_min_host, lo, (size_t)n_queries * 8, cudaMemcpyDeviceToHost, s));
     LT_CUDA(cudaMemcpyAsync(tp_max_host, hi, (size_t)n_queries * 8, cudaMemcpyDeviceToHost, s));
     LT_CUDA(cudaStreamSynchronize(s));
+    return LT_OK;
+}
+
+extern "C" int lt_rank_curve(const float* scores, const uint8_t* labels, int64_t n_pairs, float* thresholds,
+                             int64_t* tps, int64_t* fps, int64_t cap, int64_t* n_points_host, lt_stream_t stream) {
+    LT_CHECK_ARG(scores && labels && n_pairs > 0 && n_points_host, "lt_rank_curve");
+    cudaStream_t s = (cudaStream_t)stream;
+    Scratch scratch(s);
+    Ranking rk;
+    LT_TRY(build_ranking(scratch, scores, labels, n_pairs, &rk, s));
+    *n_points_host = rk.G;
+    if (rk.G > cap || !thresholds || !tps || !fps) {
+        if (cap == 0) return LT_OK;   // size query
+        set_error("lt_rank_curve: %d curve points exceed capacity %lld", rk.G, (long long)cap);
+        return LT_ERR_CAPACITY;
+    }
+    k_rank_curve<<<(unsigned)ceil_div(rk.G, 256), 256, 0, s>>>(rk.keys, rk.gstart, rk.G, rk.tp_excl, thresholds, tps, fps);
+    LT_LAUNCH_CHECK();
+    LT_CUDA(cudaStreamSynchronize(s));   // scratch (keys) must outlive the kernel's reads of it: freed stream-ordered anyway
     return LT_OK;
 }

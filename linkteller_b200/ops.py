@@ -384,6 +384,24 @@ def topk_tp(scores: torch.Tensor, labels: torch.Tensor, n_pos):
     return list(lo), list(hi)
 
 
+def rank_curve(scores: torch.Tensor, labels: torch.Tensor):
+    """sklearn's _binary_clf_curve on the device: (thresholds float32, tps int64, fps int64), one point
+    per distinct score, scores descending."""
+    lib = _lib.load()
+    _chk(scores, torch.float32, "scores", 1)
+    _chk(labels, torch.uint8, "labels", 1)
+    n = scores.numel()
+    g = C.c_int64()
+    _lib.check(lib.lt_rank_curve(_p(scores), _p(labels), n, None, None, None, 0, C.byref(g), _stream()), "lt_rank_curve")
+    G = g.value
+    thr = torch.empty(G, dtype=torch.float32, device=scores.device)
+    tps = torch.empty(G, dtype=torch.int64, device=scores.device)
+    fps = torch.empty(G, dtype=torch.int64, device=scores.device)
+    _lib.check(lib.lt_rank_curve(_p(scores), _p(labels), n, _p(thr), _p(tps), _p(fps), G, C.byref(g), _stream()),
+               "lt_rank_curve")
+    return thr, tps, fps
+
+
 # ------------------------------------------------------------------------------------------ a10
 LSA2_TRANSFORMS = {"none": 0, "softmax": 1, "sigmoid": 2}
 
@@ -400,6 +418,47 @@ def lsa2_corr(mat: torch.Tensor, test_nodes: torch.Tensor, transform: str = "non
     _lib.check(lib.lt_lsa2_corr(_p(mat), ldm, mat.shape[1], _p(test_nodes), T, LSA2_TRANSFORMS[transform], _p(dist), T,
                                 _stream()), "lt_lsa2_corr")
     return dist
+
+
+# ------------------------------------------------------------------------------------------ a11/a12
+def dp_edgerand_apply(adj: DeviceCSR, hits: torch.Tensor, coin: torch.Tensor) -> DeviceCSR:
+    """adj + add − minus with −1→0, 2→1 (worker.py:264-267) from host-drawn flips.  hits: int64 cell
+    ids r*n+c (r<c, ascending); coin: uint8 (1 = add).  Output values float64 (scipy promotes)."""
+    lib = _lib.load()
+    _chk(hits, torch.int64, "hits", 1)
+    _chk(coin, torch.uint8, "coin", 1)
+    vals = adj.values.to(torch.float64).contiguous()
+    n, k = adj.n, hits.numel()
+    cap = max(adj.nnz + 2 * k, 1)
+    dev = vals.device
+    oip = torch.empty(n + 1, dtype=torch.int32, device=dev)
+    oix = torch.empty(cap, dtype=torch.int32, device=dev)
+    ov = torch.empty(cap, dtype=torch.float64, device=dev)
+    nnz = C.c_int64()
+    _lib.check(lib.lt_dp_edgerand_apply(_p(adj.indptr), _p(adj.indices), _p(vals), n, _p(hits), _p(coin), k, _p(oip),
+                                        _p(oix), _p(ov), cap, C.byref(nnz), _stream()), "lt_dp_edgerand_apply")
+    return DeviceCSR(oip, oix[:nnz.value], ov[:nnz.value], n)
+
+
+def dp_lapgraph_select(adj: DeviceCSR, noise: torch.Tensor, n_keep: int) -> DeviceCSR:
+    """Top-n_keep cells of tril(adj,-1)+noise → symmetric binary CSR (worker.py:298-335).  `noise`
+    ([n,n] float64, device) is consumed.  Values are float64 ones so that the normalisation that
+    follows runs in float64 like the reference's int32 matrix does."""
+    lib = _lib.load()
+    _chk(noise, torch.float64, "noise", 2)
+    n = adj.n
+    if tuple(noise.shape) != (n, n):
+        raise ValueError("noise must be [n,n]")
+    vals = adj.values.to(torch.float64).contiguous()
+    cap = max(2 * int(n_keep), 1)
+    dev = vals.device
+    oip = torch.empty(n + 1, dtype=torch.int32, device=dev)
+    oix = torch.empty(cap, dtype=torch.int32, device=dev)
+    ov = torch.empty(cap, dtype=torch.float32, device=dev)
+    nnz = C.c_int64()
+    _lib.check(lib.lt_dp_lapgraph_select(_p(adj.indptr), _p(adj.indices), _p(vals), n, _p(noise), int(n_keep), _p(oip),
+                                         _p(oix), _p(ov), cap, C.byref(nnz), _stream()), "lt_dp_lapgraph_select")
+    return DeviceCSR(oip, oix[:nnz.value], ov[:nnz.value].to(torch.float64), n)
 
 
 # ------------------------------------------------------------------------------------------ primitives (tests)

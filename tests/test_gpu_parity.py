@@ -352,3 +352,51 @@ def test_a10_lsa2(ops, golden, case):
         # float32 dot/norm in a different summation order than torch's: 2e-5 relative, 2e-6 absolute
         np.testing.assert_allclose(pick(g["a6_exist"]), g[f"a10_{key}_exist"], rtol=2e-5, atol=2e-6)
         np.testing.assert_allclose(pick(g["a6_nonexist"]), g[f"a10_{key}_nonexist"], rtol=2e-5, atol=2e-6)
+
+
+# ------------------------------------------------------------------------------------ a11/a12
+def test_a11_edgerand_bit_exact(ops, golden):
+    from linkteller_b200 import dp
+    g = golden("tiny_edgerand")
+    s, _ = case_inputs(g)
+    ori = ops.DeviceCSR(dev(g["a1_indptr"]), dev(g["a1_indices"]), dev(g["a1_data"]), s.n)
+    out = dp.perturb_adj(ori, "discrete", float(g["epsilon"]), int(g["noise_seed"]))
+    assert np.array_equal(out.indptr.cpu().numpy(), g["dp_indptr"])
+    assert np.array_equal(out.indices.cpu().numpy(), g["dp_indices"])
+    assert np.array_equal(out.values.cpu().numpy(), g["dp_data"]) and (g["dp_data"] == 0).any()
+    # … and the normalisation that follows prunes the explicit zeros exactly like the reference
+    hat = ops.normalize_adj(out, "FirstOrderGCN")
+    ip, ix, v = O.coo_to_csr(g["a2_row"], g["a2_col"], g["a2_val"], s.n)
+    assert np.array_equal(hat.indptr.cpu().numpy(), ip) and np.array_equal(hat.indices.cpu().numpy(), ix)
+    assert np.array_equal(hat.values.cpu().numpy().view(np.uint32), v.view(np.uint32))
+
+
+def test_a12_lapgraph_bit_exact(ops, golden):
+    from linkteller_b200 import dp
+    g = golden("tiny_lapgraph")
+    s, _ = case_inputs(g)
+    ori = ops.DeviceCSR(dev(g["a1_indptr"]), dev(g["a1_indices"]), dev(g["a1_data"]), s.n)
+    out = dp.perturb_adj(ori, "continuous", float(g["epsilon"]), int(g["noise_seed"]))
+    assert np.array_equal(out.indptr.cpu().numpy(), g["dp_indptr"])
+    assert np.array_equal(out.indices.cpu().numpy(), g["dp_indices"])
+    assert np.array_equal(out.values.cpu().numpy(), g["dp_data"].astype(np.float64))
+    hat = ops.normalize_adj(out, "FirstOrderGCN")
+    ip, ix, v = O.coo_to_csr(g["a2_row"], g["a2_col"], g["a2_val"], s.n)
+    assert np.array_equal(hat.indptr.cpu().numpy(), ip) and np.array_equal(hat.indices.cpu().numpy(), ix)
+    assert np.array_equal(hat.values.cpu().numpy().view(np.uint32), v.view(np.uint32))
+
+
+@pytest.mark.parametrize("kind", ["discrete", "continuous"])
+def test_a11_a12_twitch_size_vs_oracle(ops, kind):
+    # full C4 size (n=4385): device apply vs the oracle's numpy restatement, same seed
+    from linkteller_b200 import dp
+    s = synth.make("twitch", seed=0)
+    ori = ops.csr_from_edges(dev(s.edges), s.n)
+    out = dp.perturb_adj(ori, kind, 5.0, 42)
+    ip, ix, dv = ori.indptr.cpu().numpy(), ori.indices.cpu().numpy(), ori.values.cpu().numpy()
+    if kind == "discrete":
+        rip, rix, rdv = O.edgerand(ip, ix, dv, s.n, 5.0, 42)
+    else:
+        rip, rix, rdv, _ = O.lapgraph(ip, ix, dv, s.n, 5.0, 42)
+    assert np.array_equal(out.indptr.cpu().numpy(), rip) and np.array_equal(out.indices.cpu().numpy(), rix)
+    assert np.array_equal(out.values.cpu().numpy(), rdv.astype(np.float64))

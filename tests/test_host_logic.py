@@ -1,0 +1,117 @@
+"""CPU-side tests of the host logic above the C ABI: curve assembly, pair lists, row sharding and
+the all-gather of influence rows (gloo, world_size 2), the host halves of the DP mechanisms."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from linkteller_b200 import attack, dp, workloads
+from linkteller_b200.attacker import PairList, binary_clf_curves
+from oracle import lt_oracle as O
+
+
+def clf_counts(y, pred):
+    """numpy restatement of sklearn's _binary_clf_curve (what lt_rank_curve returns)."""
+    order = np.argsort(-pred, kind="stable")
+    ys, ps = y[order], pred[order]
+    last = np.r_[np.where(np.diff(ps))[0], len(ps) - 1]
+    tps = np.cumsum(ys)[last]
+    fps = 1 + last - tps
+    return ps[last], tps, fps
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_curves_match_sklearn(seed):
+    from sklearn import metrics
+    rng = np.random.default_rng(seed)
+    n = 5000
+    pred = np.where(rng.random(n) < 0.7, 0.0, np.round(rng.random(n), 2)).astype(np.float32).astype(np.float64)
+    y = (rng.random(n) < 0.1 + 0.5 * pred).astype(np.int64)
+    (fpr, tpr, thr), (prec, rec, thr2) = binary_clf_curves(*clf_counts(y, pred))
+    f0, t0, th0 = metrics.roc_curve(y, pred)
+    p0, r0, th20 = metrics.precision_recall_curve(y, pred)
+    assert np.array_equal(fpr, f0) and np.array_equal(tpr, t0) and np.array_equal(thr, th0)
+    assert np.array_equal(prec, p0) and np.array_equal(rec, r0) and np.array_equal(thr2, th20)
+
+
+def test_curves_match_golden_reference_run(golden):
+    g = golden("small_hi")
+    pred = np.concatenate([g["a8_exist32"], g["a8_nonexist32"]])
+    (fpr, tpr, _), _ = binary_clf_curves(*clf_counts(g["a9_y"], pred))
+    assert np.array_equal(fpr, g["a9_fpr"]) and np.array_equal(tpr, g["a9_tpr"])
+
+
+def test_pair_list_behaves_like_list_of_tuples():
+    p = PairList(np.array([[3, 9], [4, 1]]))
+    assert len(p) == 2 and list(p) == [(3, 9), (4, 1)] and p[1] == (4, 1)
+    assert np.asarray(p).shape == (2, 2)
+    assert len(PairList(np.zeros((0, 2)))) == 0
+
+
+@pytest.mark.parametrize("T,world", [(8192, 8), (500, 4), (7, 3), (2, 4), (2000, 1)])
+def test_slice_bounds_partition(T, world):
+    b = [attack.slice_bounds(T, world, r) for r in range(world)]
+    assert b[0][0] == 0 and b[-1][1] == T
+    assert all(b[r][1] == b[r + 1][0] for r in range(world - 1))
+    sizes = [hi - lo for lo, hi in b]
+    assert max(sizes) - min(sizes) <= 1
+
+
+def _gather_worker(rank, world, T, port, ok):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    full = torch.arange(T * T, dtype=torch.float32).reshape(T, T)
+    out = torch.full((T, T), -1.0)
+    lo, hi = attack.slice_bounds(T, world, rank)
+    out[lo:hi] = full[lo:hi]                       # this rank's influence rows
+    attack.gather_rows(out, T, world)
+    ok[rank] = int(torch.equal(out, full))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("T", [8, 7])               # equal slices (one all-gather) and ragged slices
+def test_gather_rows_gloo_world2(T):
+    import torch.multiprocessing as mp
+    ok = mp.get_context("spawn").Array("i", [0, 0])
+    port = 29500 + (os.getpid() + T) % 500
+    mp.spawn(_gather_worker, args=(2, T, port, ok), nprocs=2, join=True)
+    assert list(ok) == [1, 1]
+
+
+def test_sampling_matches_oracle_and_reference_stream(golden):
+    g = golden("small_hi")
+    tn = workloads.sample_test_nodes_typed(str(g["dataset"]), str(g["sample_type"]), g["a1_indptr"], int(g["T"]), 42)
+    assert np.array_equal(tn, g["a6_test_nodes"])
+    g = golden("tiny_fo")
+    tn = workloads.sample_test_nodes_typed(str(g["dataset"]), "unbalanced", g["a1_indptr"], int(g["T"]), 42)
+    assert np.array_equal(tn, g["a6_test_nodes"])
+    with pytest.raises(NotImplementedError):
+        workloads.sample_test_nodes_typed("nope", "unbalanced-lo", g["a1_indptr"], 5, 42)
+    with pytest.raises(ValueError):
+        workloads.sample_test_nodes_typed("ppi", "unbalanced-hi", g["a1_indptr"], 10 ** 6, 42)
+
+
+def test_dp_host_halves_match_oracle_streams(golden):
+    g = golden("tiny_edgerand")
+    n = len(g["a1_indptr"]) - 1
+    hits, coin = dp.edgerand_flips(n, float(g["epsilon"]), 42)
+    assert (np.diff(hits) > 0).all() and ((hits // n) < (hits % n)).all() and set(np.unique(coin)) <= {0, 1}
+    # same stream as the oracle's restatement: applying the flips with numpy reproduces its result
+    ip, ix, dv = O.edgerand(g["a1_indptr"], g["a1_indices"], g["a1_data"], n, float(g["epsilon"]), 42)
+    import scipy.sparse as sp
+    A = sp.csr_matrix((g["a1_data"].astype(np.float64), g["a1_indices"], g["a1_indptr"]), shape=(n, n))
+    r, c = hits // n, hits % n
+    add = sp.csr_matrix((np.ones(int(coin.sum())), (r[coin == 1], c[coin == 1])), shape=(n, n))
+    rem = sp.csr_matrix((np.ones(int((coin == 0).sum())), (r[coin == 0], c[coin == 0])), shape=(n, n))
+    out = (A + (add + add.T) - (rem + rem.T)).tocsr()
+    out.sort_indices()
+    out.data[out.data == -1] = 0
+    out.data[out.data == 2] = 1
+    assert np.array_equal(out.indptr, ip) and np.array_equal(out.indices, ix) and np.array_equal(out.data, dv)
+    g = golden("tiny_lapgraph")
+    noise, n_keep = dp.lapgraph_noise(n, len(g["a1_data"]) // 2, float(g["epsilon"]), 42)
+    assert noise.shape == (n, n) and n_keep == O.lapgraph(g["a1_indptr"], g["a1_indices"], g["a1_data"], n,
+                                                          float(g["epsilon"]), 42)[3]
