@@ -20,21 +20,19 @@ from torch.nn.parameter import Parameter
 from . import adj as _adj
 from . import ops
 
-_CSR_CACHE = weakref.WeakKeyDictionary()
+_CSR_CACHE = {}   # id(adjacency object) → (weakref to it, [Â, Âᵀ])
 
 
 def _csr_pair(adj):
-    """(Â, Âᵀ) as DeviceCSR for the `adj` argument of forward; cached per adjacency object."""
-    if isinstance(adj, ops.DeviceCSR):
-        key = adj.indptr
-    else:
-        key = adj
-    hit = _CSR_CACHE.get(key)
-    if hit is not None:
-        return hit
-    csr = _adj.device_csr_of(adj)
-    pair = [csr, None]
-    _CSR_CACHE[key] = pair
+    """[Â, Âᵀ] as DeviceCSR for the `adj` argument of forward; cached per adjacency OBJECT (identity,
+    not value: tensors do not hash/compare by content) and dropped when that object dies."""
+    key = adj.indptr if isinstance(adj, ops.DeviceCSR) else adj
+    hit = _CSR_CACHE.get(id(key))
+    if hit is not None and hit[0]() is key:
+        return hit[1]
+    pair = [_adj.device_csr_of(adj), None]
+    k = id(key)
+    _CSR_CACHE[k] = (weakref.ref(key, lambda _r, k=k: _CSR_CACHE.pop(k, None)), pair)
     return pair
 
 

@@ -53,7 +53,10 @@ def test_attacker_efficient_end_to_end(golden, case, tmp_path, monkeypatch, caps
     out = capsys.readouterr().out
     assert "auc =" in out and "attack results saved to:" in out
     # file name and schema exactly as the reference writes them (attacker.py:388-411)
-    fn = str(g["a9_filename"])
+    fn = str(g["a9_filename"])          # the golden run used mode vanilla-clean (attacker.py:391-392)
+    if args.mode != "vanilla-clean":    # DP naming, attacker.py:393-394
+        fn = (f"eval_{args.dataset}/efficient_{args.sample_type}_{args.perturb_type}_{args.n_test}_42"
+              f"_eps-{args.epsilon}_seed-42.pt")
     assert os.path.exists(fn), os.listdir(".")
     saved = torch.load(fn, weights_only=False)
     assert set(saved) == {"auc", "pr", "result"} and set(saved["auc"]) == {"fpr", "tpr", "thresholds"}
@@ -128,10 +131,11 @@ def test_get_gradient_eps_mat_matches_influence_row(golden):
     tn = att.test_nodes
     grad = att.get_gradient_eps_mat(int(tn[3])).cpu().numpy()
     row = np.linalg.norm(grad[tn], axis=1)
-    # the two-forward finite difference in fp32 is the noisy one: 25 % on the support, zeros exact
+    # the two-forward finite difference in fp32 is the noisy one (errors of 3-10 % are typical,
+    # far more on small entries): zeros exact, entries above 10 % of the row maximum within 5 %
     assert np.array_equal(row == 0, infl[3] == 0)
-    nz = infl[3] != 0
-    assert (np.abs(row[nz] - infl[3][nz]) / infl[3][nz]).max() < 0.25
+    nz = infl[3] >= 0.1 * infl[3].max()
+    assert (np.abs(row[nz] - infl[3][nz]) / infl[3][nz]).max() < 0.05
 
 
 def test_gcn_modules_forward_backward_match_torch(golden):
