@@ -4,14 +4,14 @@
 //
 // algo 1: fp32 SIMT, 128x64x32 tiles, 8x4 register blocking, register-staged double buffering.
 // algo 2: 3xTF32 on the 5th-gen tensor cores (tcgen05.mma kind::tf32, TMEM accumulators) — see
-//         gemm_tc.cu; falls back to algo 1 for shapes it does not cover.
+//         gemm_tc.cu.  algo 0 (auto) picks it for products above 2^24 multiply-adds with N ≥ 16.
 #include "common.cuh"
 
 namespace lt {
 
 int gemm_3xtf32(const float* A, int64_t lda, const int32_t* a_rows, const float* B, int64_t ldb, int transB,
                 const float* bias, int relu, float* C, int64_t ldc, int32_t M, int32_t N, int32_t K,
-                cudaStream_t s, bool* handled);
+                cudaStream_t s, bool force, bool* handled);
 
 constexpr int GM_BM = 128, GM_BN = 64, GM_BK = 32, GM_THREADS = 256;
 constexpr int GM_APAD = 4;
@@ -124,7 +124,7 @@ int gemm_f32(const float* A, int64_t lda, const int32_t* a_rows, const float* B,
     if (M == 0 || N == 0) return LT_OK;
     if (algo == 0 || algo == 2) {
         bool handled = false;
-        LT_TRY(gemm_3xtf32(A, lda, a_rows, B, ldb, transB, bias, relu, C, ldc, M, N, K, s, &handled));
+        LT_TRY(gemm_3xtf32(A, lda, a_rows, B, ldb, transB, bias, relu, C, ldc, M, N, K, s, algo == 2, &handled));
         if (handled) return LT_OK;
         if (algo == 2) {
             set_error("lt_gemm_f32: algo=2 (3xTF32 tensor cores) does not cover M=%d N=%d K=%d transB=%d", M, N, K,
