@@ -17,7 +17,7 @@
 //   F1 k_frontier_dq     : ΔQ[e,:] for every incidence      (reads one H row per incidence: HBM-bound
 //                          on large graphs; a [64 x h]·[h x c] register-blocked product per CTA)
 //   F2 k_frontier_reduce : out[j,i] = ‖Σ_k w_k·ΔQ[e_k,:]‖₂  (segmented, deterministic)
-#include "common.cuh"
+#include "gemm_tc.cuh"
 
 namespace lt {
 
@@ -299,7 +299,7 @@ k_frontier_dq(const int32_t* __restrict__ s_j, const int32_t* __restrict__ s_rho
 constexpr int F2_BIG = 64;
 constexpr int F2_BIG_WARPS = 32;   // 1024-thread CTA per big group
 
-__device__ __forceinline__ float f2_column(const uint64_t* __restrict__ val, const float* __restrict__ dq, int32_t c,
+__device__ __forceinline__ float f2_column(const uint64_t* __restrict__ val, const float* __restrict__ dq, int32_t c /* row stride of dq */,
                                            int col, int32_t m0, int32_t m1) {
     float z0 = 0.f, z1 = 0.f, z2 = 0.f, z3 = 0.f;
     int32_t m = m0;
@@ -323,7 +323,7 @@ template <int G>
 __global__ void __launch_bounds__(256)
 k_frontier_reduce(const uint64_t* __restrict__ key, const uint64_t* __restrict__ val,
                   const int32_t* __restrict__ grp_off, const int32_t* __restrict__ n_groups,
-                  const float* __restrict__ dq, int32_t c, float* __restrict__ out, int64_t ldo) {
+                  const float* __restrict__ dq, int32_t lddq, int32_t c, float* __restrict__ out, int64_t ldo) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t g = t / G;
     const int sub = (int)(t % G);
@@ -337,7 +337,7 @@ k_frontier_reduce(const uint64_t* __restrict__ key, const uint64_t* __restrict__
         } else {
             k0 = key[m0];
             for (int col = sub; col < c; col += G) {
-                const float z = f2_column(val, dq, c, col, m0, m1);
+                const float z = f2_column(val, dq, lddq, col, m0, m1);
                 ss = fmaf(z, z, ss);
             }
         }
@@ -360,7 +360,7 @@ __global__ void k_big_groups(const int32_t* __restrict__ grp_off, const int32_t*
 __global__ void __launch_bounds__(32 * F2_BIG_WARPS)
 k_frontier_reduce_big(const uint64_t* __restrict__ key, const uint64_t* __restrict__ val,
                       const int32_t* __restrict__ grp_off, const int32_t* __restrict__ big,
-                      const int32_t* __restrict__ n_big, const float* __restrict__ dq, int32_t c,
+                      const int32_t* __restrict__ n_big, const float* __restrict__ dq, int32_t lddq, int32_t c,
                       float* __restrict__ out, int64_t ldo) {
     __shared__ float part[F2_BIG_WARPS][32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -372,7 +372,7 @@ k_frontier_reduce_big(const uint64_t* __restrict__ key, const uint64_t* __restri
         float ss = 0.f;   // meaningful in warp 0 only
         for (int c0 = 0; c0 < c; c0 += 32) {
             const int col = c0 + lane;
-            part[warp][lane] = col < c ? f2_column(val, dq, c, col, a0, a1) : 0.f;
+            part[warp][lane] = col < c ? f2_column(val, dq, lddq, col, a0, a1) : 0.f;
             __syncthreads();
             if (warp == 0) {
                 float z = 0.f;
@@ -391,6 +391,25 @@ k_frontier_reduce_big(const uint64_t* __restrict__ key, const uint64_t* __restri
         }
     }
 }
+
+// A operand of the tensor-core F1: row e of ΔR, computed from one H row, one P row and a_e
+struct DeltaRProd {
+    const int32_t* s_j; const int32_t* s_rho; const float* s_a; const int32_t* p_index;
+    const float* H; int64_t ldh; const float* P; int64_t ldp; float delta, inv_delta;
+    __device__ __forceinline__ void meta(int e, int64_t& o0, int64_t& o1, float& f) const {
+        const int32_t j = s_j[e];
+        o0 = (int64_t)s_rho[e] * ldh;
+        o1 = (int64_t)(p_index ? p_index[j] : j) * ldp;
+        f = s_a[e];
+    }
+    __device__ __forceinline__ TcRaw raw(int64_t o0, int64_t o1, int k) const { return TcRaw{__ldg(H + o0 + k), __ldg(P + o1 + k)}; }
+    __device__ __forceinline__ float value(TcRaw r, float a) const {
+        const float hh = r.x, p = r.y;
+        const float hp = fmaf(delta * a, p, hh);           // H'[r,k]
+        if (hh > 0.f) return hp > 0.f ? a * p : -hh * inv_delta;
+        return hp > 0.f ? hp * inv_delta : 0.f;
+    }
+};
 
 static int plan_own(lt_plan* p, void* ptr) {
     if (p->n_owned >= 24) { set_error("plan: too many buffers"); return LT_ERR_INTERNAL; }
@@ -546,9 +565,28 @@ int influence_rows(const lt_plan* p, const float* H_R, int64_t ldh, const float*
     }
     Scratch scratch(s);
     float* dq;
-    LT_TRY(scratch.alloc(&dq, (size_t)E * c));
-    const unsigned bl = (unsigned)ceil_div(E, F1_TILE_E);
     const float inv_delta = 1.0f / delta;
+    // ΔQ = ΔR·W2: on the tensor cores (3xTF32, tcgen05) when the product is large enough, else fp32 SIMT
+    const bool use_tc = c <= 256 && c >= 8 && E * (int64_t)h * c >= ((int64_t)1 << 24);
+    const int32_t lddq = use_tc ? (c + 3) / 4 * 4 : c;
+    LT_TRY(scratch.alloc(&dq, (size_t)E * lddq));
+    if (use_tc) {
+        ProfScope prof("frontier_dq", s);
+        const int nt = tc_pick_nt(c);
+        const int32_t n_pad = nt, kchunks = (h + TC_BK - 1) / TC_BK;
+        uint32_t* img;
+        LT_TRY(scratch.alloc(&img, (size_t)kchunks * 2 * n_pad * TC_BK));
+        LT_TRY(tc_prepack_b(W2, c, 0, c, h, n_pad, img, s));
+        const DeltaRProd prod{p->s_j, p->s_rho, p->s_a, p_index, H_R, ldh, P, ldp, delta, inv_delta};
+        switch (nt) {
+            case 32: LT_TRY((launch_tc<32, 2>(prod, img, nullptr, 0, dq, lddq, (int32_t)E, c, h, n_pad, kchunks, s))); break;
+            case 48: LT_TRY((launch_tc<48, 2>(prod, img, nullptr, 0, dq, lddq, (int32_t)E, c, h, n_pad, kchunks, s))); break;
+            case 64: LT_TRY((launch_tc<64, 2>(prod, img, nullptr, 0, dq, lddq, (int32_t)E, c, h, n_pad, kchunks, s))); break;
+            case 128: LT_TRY((launch_tc<128, 1>(prod, img, nullptr, 0, dq, lddq, (int32_t)E, c, h, n_pad, kchunks, s))); break;
+            default: LT_TRY((launch_tc<256, 1>(prod, img, nullptr, 0, dq, lddq, (int32_t)E, c, h, n_pad, kchunks, s))); break;
+        }
+    } else {
+    const unsigned bl = (unsigned)ceil_div(E, F1_TILE_E);
     for (int32_t c0 = 0; c0 < c; c0 += 128) {
         ProfScope prof("frontier_dq", s);
         const int32_t cw = c - c0 < 128 ? c - c0 : 128;
@@ -567,10 +605,11 @@ int influence_rows(const lt_plan* p, const float* H_R, int64_t ldh, const float*
 #undef LT_F1
         LT_LAUNCH_CHECK();
     }
+    }
     ProfScope prof2("frontier_reduce", s);
 #define LT_F2(G_)                                                                                              \
     k_frontier_reduce<G_><<<(unsigned)ceil_div(M * G_, 256), 256, 0, s>>>(p->rec_key, p->rec_val, p->grp_off,  \
-                                                                          p->n_groups, dq, c, out, ldo)
+                                                                          p->n_groups, dq, lddq, c, out, ldo)
     if (c <= 1) LT_F2(1);
     else if (c <= 2) LT_F2(2);
     else if (c <= 4) LT_F2(4);
@@ -581,7 +620,7 @@ int influence_rows(const lt_plan* p, const float* H_R, int64_t ldh, const float*
     LT_LAUNCH_CHECK();
     if (M > F2_BIG) {
         k_frontier_reduce_big<<<(unsigned)num_sms() * 2, 32 * F2_BIG_WARPS, 0, s>>>(p->rec_key, p->rec_val, p->grp_off, p->big, p->n_big,
-                                                                     dq, c, out, ldo);
+                                                                     dq, lddq, c, out, ldo);
         LT_LAUNCH_CHECK();
     }
     return LT_OK;

@@ -1,0 +1,299 @@
+// tcgen05 3xTF32 GEMM building block shared by gemm_tc.cu (plain A operand) and frontier.cu (A operand
+// = ΔR computed on the fly).  See gemm_tc.cu for the design notes.
+#pragma once
+#include "common.cuh"
+
+namespace lt {
+
+constexpr int TC_BM = 128;        // rows per tile = UMMA M (cta_group::1)
+constexpr int TC_BK = 32;         // tf32 elements per K chunk = one 128-byte swizzle atom
+constexpr int TC_THREADS = 256;
+constexpr int TC_STAGES = 2;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+    hi = to_tf32(x);
+    lo = to_tf32(x - __uint_as_float(hi));
+}
+
+// byte offset of element (row, k) inside a [rows x 32] K-major tile with 128-byte swizzle:
+// 8-row groups of 1024 B, 16-byte chunks XOR-ed with the row index inside the group
+__host__ __device__ __forceinline__ uint32_t sw128_offset(int row, int k) {
+    return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((((k >> 2) ^ (row & 7)) & 7) << 4) + ((k & 3) << 2));
+}
+
+// shared-memory matrix descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 B apart (SBO), version 1
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);          // start address       bits [0,14)
+    d |= (uint64_t)1 << 16;                           // leading byte offset bits [16,30) (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;                 // stride byte offset  bits [32,46)
+    d |= (uint64_t)1 << 46;                           // descriptor version  bits [46,48)
+    d |= (uint64_t)2 << 61;                           // SWIZZLE_128B        bits [61,64)
+    return d;
+}
+// instruction descriptor: D=F32, A=B=TF32, both K-major, N>>3 at [17,23), M>>4 at [24,29)
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// A-operand producers.  A producer describes how element (row m, column k) of the A operand is
+// obtained: per-row metadata (two offsets and a scalar, kept in shared memory per tile), the raw
+// global loads for one element (prefetched one K chunk ahead) and the value computed from them.
+struct TcRaw { float x, y; };
+
+struct PlainA {   // A[m,k] = A[a_rows ? a_rows[m] : m][k]
+    const float* A; int64_t lda; const int32_t* a_rows;
+    __device__ __forceinline__ void meta(int m, int64_t& o0, int64_t& o1, float& f) const {
+        o0 = (int64_t)(a_rows ? a_rows[m] : m) * lda; o1 = 0; f = 0.f;
+    }
+    __device__ __forceinline__ TcRaw raw(int64_t o0, int64_t, int k) const { return TcRaw{__ldg(A + o0 + k), 0.f}; }
+    __device__ __forceinline__ float value(TcRaw r, float) const { return r.x; }
+};
+
+struct TcSmem {
+    static constexpr int A_TILE = TC_BM * TC_BK * 4;    // 16 KB
+};
+
+template <int NT>
+constexpr size_t tc_smem_bytes() { return (size_t)TC_STAGES * (2 * TcSmem::A_TILE + 2 * NT * TC_BK * 4) + 1024; }
+
+// C[M,N] = Aop[M,K]·B (+bias) (ReLU), B given as the packed image of k_tc_prepack_b.
+template <int NT, int MINB, class Prod>
+__global__ void __launch_bounds__(TC_THREADS, MINB)
+k_gemm_tc(Prod prod, const uint32_t* __restrict__ Bimg, const float* __restrict__ bias, int relu, float* __restrict__ C,
+          int64_t ldc, int32_t M, int32_t N, int32_t K, int32_t n_pad_total, int32_t kchunks) {
+    constexpr int B_TILE = NT * TC_BK * 4;
+    constexpr int STAGE = 2 * TcSmem::A_TILE + 2 * B_TILE;
+    constexpr int TMEM_COLS = NT <= 32 ? 32 : NT <= 64 ? 64 : NT <= 128 ? 128 : 256;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    __shared__ uint64_t tma_bar[TC_STAGES], mma_bar[TC_STAGES];
+    __shared__ uint32_t tmem_base_s;
+    __shared__ int64_t meta0[2][TC_BM], meta1[2][TC_BM];
+    __shared__ float meta2[2][TC_BM];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&tma_bar[s], 1); mbar_init(&mma_bar[s], 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
+                     "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    const int n0 = blockIdx.y * NT;                          // first column of this CTA's N tile
+    const int tiles_m = (M + TC_BM - 1) / TC_BM;
+    const int my_tiles = blockIdx.x < tiles_m ? (tiles_m - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+
+    auto load_meta = [&](int tile_idx) {                     // threads 0..127: metadata of tile #tile_idx of this CTA
+        if (tid < TC_BM && tile_idx < my_tiles) {
+            const int m = (blockIdx.x + tile_idx * gridDim.x) * TC_BM + tid;
+            int64_t o0 = -1, o1 = 0; float f = 0.f;
+            if (m < M) prod.meta(m, o0, o1, f);
+            meta0[tile_idx & 1][tid] = o0; meta1[tile_idx & 1][tid] = o1; meta2[tile_idx & 1][tid] = f;
+        }
+    };
+    load_meta(0);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_s;
+    constexpr uint32_t idesc = make_idesc(TC_BM, NT);
+
+    // raw operands of the NEXT chunk, prefetched while the tensor core works on the current one:
+    // this warp stages rows warp*16 .. +15, lane ↔ k inside the chunk
+    TcRaw pre[16];
+    auto prefetch = [&](int tile_idx, int kc) {
+        const int k = kc * TC_BK + lane;
+        const int b = tile_idx & 1;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const int64_t o0 = meta0[b][warp * 16 + q];
+            pre[q] = (o0 >= 0 && k < K) ? prod.raw(o0, meta1[b][warp * 16 + q], k) : TcRaw{0.f, 0.f};
+        }
+    };
+    const uint32_t total = (uint32_t)my_tiles * (uint32_t)kchunks;
+    if (total) prefetch(0, 0);
+
+    int tile_idx = 0, kc = 0;
+    for (uint32_t it = 0; it < total; ++it) {
+        const int s = it & 1;
+        const uint32_t use = it >> 1;
+        uint8_t* st = smem + (size_t)s * STAGE;
+        uint8_t* a_hi = st;
+        uint8_t* a_lo = st + TcSmem::A_TILE;
+        uint8_t* b_hi = st + 2 * TcSmem::A_TILE;            // [hi | lo] contiguous, as in the packed image
+        if (use > 0) mbar_wait(&mma_bar[s], (use - 1) & 1);  // MMAs that read this stage have completed
+        if (tid == 0) {
+            mbar_expect_tx(&tma_bar[s], 2 * B_TILE);
+            const uint32_t* src = Bimg + (size_t)kc * 2 * n_pad_total * TC_BK;
+            bulk_g2s(b_hi, src + (size_t)n0 * TC_BK, B_TILE, &tma_bar[s]);
+            bulk_g2s(b_hi + B_TILE, src + ((size_t)n_pad_total + n0) * TC_BK, B_TILE, &tma_bar[s]);
+        }
+        {
+            const int b = tile_idx & 1;
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                const float v = prod.value(pre[q], meta2[b][warp * 16 + q]);
+                uint32_t hi, lo;
+                split_tf32(v, hi, lo);
+                const uint32_t off = sw128_offset(warp * 16 + q, lane);
+                *reinterpret_cast<uint32_t*>(a_hi + off) = hi;
+                *reinterpret_cast<uint32_t*>(a_lo + off) = lo;
+            }
+        }
+        if (kc == 0) load_meta(tile_idx + 1);                // visible after this iteration's barrier
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores → async proxy
+        __syncthreads();
+        if (tid == 0) {
+            mbar_wait(&tma_bar[s], use & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint64_t da_hi = make_smem_desc(smem_u32(a_hi)), da_lo = make_smem_desc(smem_u32(a_lo));
+            const uint64_t db_hi = make_smem_desc(smem_u32(b_hi)), db_lo = make_smem_desc(smem_u32(b_hi + B_TILE));
+#pragma unroll
+            for (int ks = 0; ks < TC_BK / 8; ++ks) {
+                const uint64_t adv = (uint64_t)((ks * 8 * 4) >> 4);     // +32 bytes per K step inside the swizzle atom
+                umma_tf32(tmem_base, da_hi + adv, db_hi + adv, idesc, (kc | ks) ? 1u : 0u);
+                umma_tf32(tmem_base, da_hi + adv, db_lo + adv, idesc, 1u);
+                umma_tf32(tmem_base, da_lo + adv, db_hi + adv, idesc, 1u);
+            }
+            umma_commit(&mma_bar[s]);
+        }
+        // next chunk's global loads fly while the MMAs run (and, at a tile end, during the epilogue)
+        const bool tile_end = kc + 1 == kchunks;
+        if (it + 1 < total) prefetch(tile_end ? tile_idx + 1 : tile_idx, tile_end ? 0 : kc + 1);
+        if (tile_end) {
+            // ---- epilogue: the last commit covers every MMA of the tile
+            mbar_wait(&mma_bar[s], use & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            // warp w may only touch TMEM lanes 32·(w%4)…+31; warps 4-7 take the upper column half when the
+            // tile is wide enough to split (NT ≥ 64)
+            constexpr int HALVES = NT >= 64 ? 2 : 1;
+            constexpr int COLS_PER_HALF = NT / HALVES;
+            const int q = warp & 3, half = warp >> 2;
+            const int m = (blockIdx.x + tile_idx * gridDim.x) * TC_BM + q * 32 + lane;
+            const bool vec4 = (ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+            if (half < HALVES) {
+#pragma unroll 1
+                for (int c0 = half * COLS_PER_HALF; c0 < (half + 1) * COLS_PER_HALF; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+                    if (m < M) {
+                        float* dst = C + (int64_t)m * ldc;
+                        const int lim = min((half + 1) * COLS_PER_HALF - c0, 32);   // valid columns of this load
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const int col = n0 + c0 + j;
+                            if (j >= lim || col >= N) continue;
+                            float x[4];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                x[u] = __uint_as_float(v[j + u]);
+                                if (bias && col + u < N) x[u] += __ldg(bias + col + u);
+                                if (relu) x[u] = fmaxf(x[u], 0.f);
+                            }
+                            if (vec4 && j + 4 <= lim && col + 4 <= N) {
+                                *reinterpret_cast<float4*>(dst + col) = make_float4(x[0], x[1], x[2], x[3]);
+                            } else {
+#pragma unroll
+                                for (int u = 0; u < 4; ++u)
+                                    if (j + u < lim && col + u < N) dst[col + u] = x[u];
+                            }
+                        }
+                    }
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncthreads();      // TMEM fully read before the next tile's first MMA overwrites it
+            kc = 0;
+            ++tile_idx;
+        } else {
+            ++kc;
+        }
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    }
+}
+
+// launch over M tiles (persistent CTAs) x N tiles; img = packed B of k_tc_prepack_b
+template <int NT, int MINB, class Prod>
+static int launch_tc(const Prod& prod, const uint32_t* img, const float* bias, int relu, float* C, int64_t ldc, int32_t M,
+                     int32_t N, int32_t K, int32_t n_pad, int32_t kchunks, cudaStream_t s) {
+    const size_t smem = tc_smem_bytes<NT>();
+    LT_CUDA(cudaFuncSetAttribute(k_gemm_tc<NT, MINB, Prod>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int tiles_m = (M + TC_BM - 1) / TC_BM;
+    const int n_tiles = n_pad / NT;
+    int gx = num_sms() * MINB / n_tiles;
+    if (gx < 1) gx = 1;
+    if (gx > tiles_m) gx = tiles_m;
+    k_gemm_tc<NT, MINB, Prod><<<dim3((unsigned)gx, (unsigned)n_tiles), TC_THREADS, smem, s>>>(prod, img, bias, relu, C, ldc, M,
+                                                                                            N, K, n_pad, kchunks);
+    LT_LAUNCH_CHECK();
+    return LT_OK;
+}
+
+// N tile used for an output width (a few instantiated widths only) and the padded width
+static inline int tc_pick_nt(int N) {
+    if (N > 256) return 256;
+    int nt = (N + 15) / 16 * 16;
+    return nt <= 32 ? 32 : nt <= 48 ? 48 : nt <= 64 ? 64 : nt <= 128 ? 128 : 256;
+}
+
+int tc_prepack_b(const float* B, int64_t ldb, int transB, int32_t N, int32_t K, int32_t n_pad, uint32_t* img, cudaStream_t s);
+
+}  // namespace lt
