@@ -92,12 +92,13 @@ int lt_adj_normalize(const int32_t* indptr, const int32_t* indices, const void* 
  *     lt_gemm_f32 : C[M,N] = A[M,K]·B (+bias[N]) (ReLU).  Row-major.  a_rows (nullable) gathers
  *                   A's rows: row m of the product uses A[a_rows[m], :].  transB != 0 reads B as
  *                   [N,K] (C = A·Bᵀ).  algo: 0 = auto, 1 = fp32 SIMT, 2 = 3xTF32 tensor cores.
- *     lt_spmm_csr_f32 : C[i,:] = Σ_k Â[r_i,k]·B[k,:] (+bias[d]) (ReLU), r_i = rows ? rows[i] : i.
+ *     lt_spmm_csr_f32 : C[i,:] = Σ_k Â[r_i,k]·B[k,:] (+bias[d]) (ReLU), r_i = rows ? rows[i] : i;
+ *                   Â is n x n, B has n rows.
  * ------------------------------------------------------------------------------------------- */
 int lt_gemm_f32(const float* A, int64_t lda, const int32_t* a_rows, const float* B, int64_t ldb,
                 int transB, const float* bias, int relu, float* C, int64_t ldc, int32_t M, int32_t N,
                 int32_t K, int algo, lt_stream_t stream);
-int lt_spmm_csr_f32(const int32_t* indptr, const int32_t* indices, const float* values,
+int lt_spmm_csr_f32(const int32_t* indptr, const int32_t* indices, const float* values, int32_t n,
                     const int32_t* rows, int32_t n_rows, const float* B, int64_t ldb, int32_t d,
                     const float* bias, int relu, float* C, int64_t ldc, lt_stream_t stream);
 

@@ -33,7 +33,7 @@ _SIGS = {
     "lt_csr_row_sums": [P, P, I32, INT, P, P],
     "lt_adj_normalize": [P, P, P, I32, INT, INT, P, P, P, P, I64, P, P],
     "lt_gemm_f32": [P, I64, P, P, I64, INT, P, INT, P, I64, I32, I32, I32, INT, P],
-    "lt_spmm_csr_f32": [P, P, P, P, I32, P, I64, I32, P, INT, P, I64, P],
+    "lt_spmm_csr_f32": [P, P, P, I32, P, I32, P, I64, I32, P, INT, P, I64, P],
     "lt_gcn_forward": [P, P, P, I32, P, I64, I32, P, P, P, P, I32, I32, P, I64, P],
     "lt_plan_create": [P, P, P, I32, P, I32, I32, I32, P, P],
     "lt_plan_destroy": [P, P],

@@ -24,9 +24,9 @@ namespace lt {
 int gemm_f32(const float* A, int64_t lda, const int32_t* a_rows, const float* B, int64_t ldb, int transB,
              const float* bias, int relu, float* C, int64_t ldc, int32_t M, int32_t N, int32_t K, int algo,
              cudaStream_t s);
-int spmm_csr_f32(const int32_t* indptr, const int32_t* indices, const float* values, const int32_t* rows,
-                 int32_t n_rows, const float* B, int64_t ldb, int32_t d, const float* bias, int relu, float* C,
-                 int64_t ldc, cudaStream_t s);
+int spmm_csr_f32(const int32_t* indptr, const int32_t* indices, const float* values, int32_t n_cols,
+                 const int32_t* rows, int32_t n_rows, const float* B, int64_t ldb, int32_t d, const float* bias, int relu,
+                 float* C, int64_t ldc, cudaStream_t s);
 
 }  // namespace lt
 
@@ -731,7 +731,7 @@ extern "C" int lt_attack_efficient(const int32_t* indptr, const int32_t* indices
                 st = scratch.alloc(&AX, (size_t)R * f);
                 if (st == LT_OK) {
                     ProfScope prof("spmm_ax", s);
-                    st = spmm_csr_f32(indptr, indices, values, plan->rows, R, X, ldx, f, nullptr, 0, AX, f, s);
+                    st = spmm_csr_f32(indptr, indices, values, n, plan->rows, R, X, ldx, f, nullptr, 0, AX, f, s);
                 }
                 if (st == LT_OK) {
                     ProfScope prof("gemm_h", s);
@@ -747,7 +747,7 @@ extern "C" int lt_attack_efficient(const int32_t* indptr, const int32_t* indices
                 }
                 if (st == LT_OK) {
                     ProfScope prof("spmm_h", s);
-                    st = spmm_csr_f32(indptr, indices, values, plan->rows, R, Pfull, h, h, b1, 0, HR, h, s);
+                    st = spmm_csr_f32(indptr, indices, values, n, plan->rows, R, Pfull, h, h, b1, 0, HR, h, s);
                 }
             }
         }

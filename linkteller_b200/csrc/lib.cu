@@ -50,9 +50,9 @@ int num_sms() {
 int gemm_f32(const float* A, int64_t lda, const int32_t* a_rows, const float* B, int64_t ldb, int transB,
              const float* bias, int relu, float* C, int64_t ldc, int32_t M, int32_t N, int32_t K, int algo,
              cudaStream_t s);
-int spmm_csr_f32(const int32_t* indptr, const int32_t* indices, const float* values, const int32_t* rows,
-                 int32_t n_rows, const float* B, int64_t ldb, int32_t d, const float* bias, int relu, float* C,
-                 int64_t ldc, cudaStream_t s);
+int spmm_csr_f32(const int32_t* indptr, const int32_t* indices, const float* values, int32_t n_cols,
+                 const int32_t* rows, int32_t n_rows, const float* B, int64_t ldb, int32_t d, const float* bias, int relu,
+                 float* C, int64_t ldc, cudaStream_t s);
 
 }  // namespace lt
 
@@ -130,8 +130,8 @@ extern "C" int lt_gcn_forward(const int32_t* indptr, const int32_t* indices, con
     LT_TRY(scratch.alloc(&Rl, (size_t)n * hp));
     LT_TRY(scratch.alloc(&Q, (size_t)n * c));
     LT_TRY(gemm_f32(X, ldx, nullptr, W1, h, 0, nullptr, 0, P, hp, n, h, f, 0, s));            // layers.py:31
-    LT_TRY(spmm_csr_f32(indptr, indices, values, nullptr, n, P, hp, h, b1, 1, Rl, hp, s));     // :32-34 + relu
+    LT_TRY(spmm_csr_f32(indptr, indices, values, n, nullptr, n, P, hp, h, b1, 1, Rl, hp, s));     // :32-34 + relu
     LT_TRY(gemm_f32(Rl, hp, nullptr, W2, c, 0, nullptr, 0, Q, c, n, c, h, 0, s));
-    LT_TRY(spmm_csr_f32(indptr, indices, values, nullptr, n, Q, c, c, b2, 0, logits, ldz, s));
+    LT_TRY(spmm_csr_f32(indptr, indices, values, n, nullptr, n, Q, c, c, b2, 0, logits, ldz, s));
     return LT_OK;
 }

@@ -225,7 +225,7 @@ def spmm(adj: DeviceCSR, b: torch.Tensor, bias: Optional[torch.Tensor] = None, r
     if bias is not None:
         _chk(bias, torch.float32, "bias", 1)
     out = torch.empty((n_rows, d), dtype=torch.float32, device=b.device)
-    _lib.check(lib.lt_spmm_csr_f32(_p(adj.indptr), _p(adj.indices), _p(adj.values), _p(rows), n_rows, _p(b), ldb, d,
+    _lib.check(lib.lt_spmm_csr_f32(_p(adj.indptr), _p(adj.indices), _p(adj.values), adj.n, _p(rows), n_rows, _p(b), ldb, d,
                                    _p(bias), int(relu), _p(out), d, _stream()), "lt_spmm_csr_f32")
     return out
 
