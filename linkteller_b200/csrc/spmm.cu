@@ -5,7 +5,7 @@
 // graph are split across warps and the hardware CTA scheduler balances the load; rows that span
 // several segments are reduced in segment order by a second tiny kernel (deterministic, no float
 // atomics).  Lanes own float4 column slices (coalesced 16 B gathers of each B row); indices and
-// values are read 32 at a time and broadcast by shuffle; 4 gathers in flight per lane.
+// values are read 32 at a time, one chunk ahead, and broadcast by shuffle; 8 gathers in flight per lane.
 #include "common.cuh"
 
 #include <stdlib.h>
@@ -15,13 +15,22 @@ namespace lt {
 constexpr int SPMM_SEG = 256;      // non-zeros per warp work item
 constexpr int SPMM_THREADS = 256;  // 8 warps per CTA
 
+// Row lists.  A product runs over list positions t = 0..n_list-1; position t stands for output row
+// il = sel ? sel[t] : t, which is matrix row r = rows ? rows[il] : il.  `sel` lets the panel path
+// split one row list into a short-row and a long-row pass without copying anything.
+__device__ __forceinline__ int32_t list_pos(const int32_t* __restrict__ sel, int64_t t) { return sel ? sel[t] : (int32_t)t; }
+
+// nseg[t] for t < *n_list (n_list_dev may be null: all n_cap positions are live), 0 beyond
 __global__ void k_spmm_segcount(const int32_t* __restrict__ indptr, const int32_t* __restrict__ rows,
-                                int32_t n_rows, int32_t seg, int32_t* __restrict__ nseg) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_rows) return;
-    const int32_t r = rows ? rows[i] : (int32_t)i;
+                                const int32_t* __restrict__ sel, const int32_t* __restrict__ n_list_dev, int32_t n_cap,
+                                int32_t seg, int32_t* __restrict__ nseg) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_cap) return;
+    if (n_list_dev && t >= *n_list_dev) { nseg[t] = 0; return; }
+    const int32_t il = list_pos(sel, t);
+    const int32_t r = rows ? rows[il] : il;
     const int32_t len = indptr[r + 1] - indptr[r];
-    nseg[i] = len <= seg ? 1 : (len + seg - 1) / seg;
+    nseg[t] = len <= seg ? 1 : (len + seg - 1) / seg;
 }
 
 __device__ __forceinline__ void fma4(float4& a, float v, const float4& x) {
@@ -29,18 +38,23 @@ __device__ __forceinline__ void fma4(float4& a, float v, const float4& x) {
 }
 
 // NV = float4 slices per lane (d ≤ 128·NV).  seg_off: exclusive scan of nseg (n_rows+1 entries).
-template <int NV, int GIF>   // GIF = gathers in flight per lane
-__global__ void __launch_bounds__(SPMM_THREADS)
+// The (column, value) pairs of the NEXT 32 non-zeros are loaded before the gathers of the current 32 are
+// issued, so a warp never waits for an index load with nothing else in flight.  Lanes keep the float4
+// index of "their" B row (32 bits — the host checks n_cols·ldb4 < 2³²), so one gather costs a shuffle,
+// a wide multiply-add and the load.
+template <int NV, int GIF, int MINB>   // GIF = gathers in flight per lane, MINB = resident CTAs per SM asked of ptxas
+__global__ void __launch_bounds__(SPMM_THREADS, MINB)
 k_spmm_vec(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices, const float* __restrict__ values,
-           const int32_t* __restrict__ rows, int32_t n_rows, const int32_t* __restrict__ seg_off,
-           const float4* __restrict__ B4, int64_t ldb4, int32_t d4, const float* __restrict__ bias, int relu,
+           const int32_t* __restrict__ rows, const int32_t* __restrict__ sel, int32_t n_rows, const int32_t* __restrict__ seg_off,
+           const float4* __restrict__ B4, uint32_t ldb4, int32_t d4, const float* __restrict__ bias, int relu,
            float* __restrict__ C, int64_t ldc, float* __restrict__ partial) {
     const int lane = threadIdx.x & 31;
     const int64_t g = ((int64_t)blockIdx.x * SPMM_THREADS + threadIdx.x) >> 5;
     const int32_t total = seg_off[n_rows];
     if (g >= total) return;
     const int32_t i = (int32_t)upper_bound(seg_off, 0, (int64_t)n_rows + 1, (int32_t)g) - 1;
-    const int32_t r = rows ? rows[i] : i;
+    const int32_t il = list_pos(sel, i);
+    const int32_t r = rows ? rows[il] : il;
     const int32_t first = seg_off[i];
     const int32_t nseg = seg_off[i + 1] - first;
     const int32_t row_beg = indptr[r], row_end = indptr[r + 1];
@@ -50,46 +64,45 @@ k_spmm_vec(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indic
     float4 acc[NV];
 #pragma unroll
     for (int q = 0; q < NV; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+    // lanes past the row width re-load the row's last float4 (same sector, result unused): a load that is
+    // predicated per lane needs a zero-fill of its destination, and that write waits for the load —
+    // which serialises the gathers (ncu: the select after each LDG was the top long_scoreboard stall)
+    const float4* Bl[NV];
+#pragma unroll
+    for (int q = 0; q < NV; ++q) Bl[q] = B4 + min(lane + 32 * q, d4 - 1);
 
+    uint32_t mo = s0 + lane < s1 ? (uint32_t)indices[s0 + lane] * ldb4 : 0u;
+    float mv = s0 + lane < s1 ? values[s0 + lane] : 0.f;
     for (int32_t base = s0; base < s1; base += 32) {
-        const int32_t my = base + lane;
-        const int32_t mc = my < s1 ? indices[my] : 0;
-        const float mv = my < s1 ? values[my] : 0.f;
+        const int32_t nx = base + 32 + lane;
+        const uint32_t no = nx < s1 ? (uint32_t)indices[nx] * ldb4 : 0u;
+        const float nv = nx < s1 ? values[nx] : 0.f;
         const int cnt = min(32, s1 - base);
-        int k = 0;
-        for (; k + GIF <= cnt; k += GIF) {
+        for (int k = 0; k < cnt; k += GIF) {
+            // every load is unconditional and lands in its own register: entries past the end of the row
+            // carry offset 0 (row 0 of B, an L1 hit) and are skipped by the warp-uniform guard below
             float4 x[GIF][NV];
-            float v[GIF];
 #pragma unroll
             for (int u = 0; u < GIF; ++u) {
-                const int32_t c = __shfl_sync(LT_FULL, mc, k + u);
-                v[u] = __shfl_sync(LT_FULL, mv, k + u);
-                const float4* src = B4 + (int64_t)c * ldb4;
+                const uint32_t o = __shfl_sync(LT_FULL, mo, (k + u) & 31);
 #pragma unroll
-                for (int q = 0; q < NV; ++q) {
-                    const int col = lane + 32 * q;
-                    x[u][q] = col < d4 ? __ldg(src + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int q = 0; q < NV; ++q) x[u][q] = __ldg(Bl[q] + o);
+            }
+#pragma unroll
+            for (int u = 0; u < GIF; ++u) {
+                const float v = __shfl_sync(LT_FULL, mv, (k + u) & 31);
+                if (k + u < cnt) {
+#pragma unroll
+                    for (int q = 0; q < NV; ++q) fma4(acc[q], v, x[u][q]);
                 }
             }
-#pragma unroll
-            for (int u = 0; u < GIF; ++u)
-#pragma unroll
-                for (int q = 0; q < NV; ++q) fma4(acc[q], v[u], x[u][q]);
         }
-        for (; k < cnt; ++k) {
-            const int32_t c = __shfl_sync(LT_FULL, mc, k);
-            const float v = __shfl_sync(LT_FULL, mv, k);
-            const float4* src = B4 + (int64_t)c * ldb4;
-#pragma unroll
-            for (int q = 0; q < NV; ++q) {
-                const int col = lane + 32 * q;
-                if (col < d4) fma4(acc[q], v, __ldg(src + col));
-            }
-        }
+        mo = no;
+        mv = nv;
     }
 
     if (nseg == 1) {
-        float* dst = C + (int64_t)i * ldc;
+        float* dst = C + (int64_t)il * ldc;
 #pragma unroll
         for (int q = 0; q < NV; ++q) {
             const int col = lane + 32 * q;
@@ -114,220 +127,219 @@ k_spmm_vec(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indic
 }
 
 // rows split over several segments: sum the partial rows in segment order, then bias / ReLU
-__global__ void k_spmm_fixup(const int32_t* __restrict__ seg_off, int32_t n_rows, const float* __restrict__ partial,
-                             int32_t d, const float* __restrict__ bias, int relu, float* __restrict__ C, int64_t ldc) {
+__global__ void k_spmm_fixup(const int32_t* __restrict__ seg_off, const int32_t* __restrict__ sel, int32_t n_rows,
+                             const float* __restrict__ partial, int32_t d, const float* __restrict__ bias, int relu,
+                             float* __restrict__ C, int64_t ldc) {
     const int lane = threadIdx.x & 31;
     const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (i >= n_rows) return;
     const int32_t first = seg_off[i], nseg = seg_off[i + 1] - first;
-    if (nseg == 1) return;
+    if (nseg <= 1) return;
+    const int64_t il = list_pos(sel, i);
     for (int col = lane; col < d; col += 32) {
         float a = 0.f;
         for (int32_t sgm = 0; sgm < nseg; ++sgm) a += partial[(int64_t)(first + sgm) * d + col];
         if (bias) a += bias[col];
         if (relu) a = fmaxf(a, 0.f);
-        C[i * ldc + col] = a;
+        C[il * ldc + col] = a;
     }
 }
 
 // ------------------------------------------------------------------------------------ panel-blocked variant
 // When the dense operand does not fit the L2 (C5: X is 0.98 GB against 126 MB), the plain kernel
-// re-fetches every gathered row from DRAM (ncu r1a: 13.8 GB of traffic for 1.4 GB of compulsory
-// bytes, L2 hit rate 10 %).  Here the columns are cut into panels whose B rows fit the L2 several
-// times over, and all resident warps walk the panels in the same order, kept within a window of
-// SPMM_WINDOW panels of each other (per-CTA progress counters in global memory; leaders wait,
-// laggards never do — the CTAs are co-resident: cooperative launch, one CTA per SM).  Each warp owns
-// 32 row segments (lane ↔ cursor into its segment; CSR rows are column-sorted, so a panel is a
-// contiguous run) whose accumulators live in shared memory (32 x d floats per warp).  Per panel a warp
-//   1. advances the 32 cursors (4-entry probes, then a binary search for long runs),
-//   2. flattens the runs into a (column | item, value) list in shared memory — load-balanced: list
-//      slot → owner lane by a binary search over the scanned run lengths,
-//   3. gathers the listed B rows cooperatively — lane ↔ float4 column slice, 16 gathers in flight —
-//      and adds them into the item's accumulator row.
-// Segments are short (SPMM_PSEG) and dealt round-robin to the CTAs so that the consecutive segments of a
-// hub row (which all fall into one or two panels) do not pile up in one warp.  Rows are written out
-// after the last panel.  A B panel is thus read from DRAM once per wave of resident rows instead of
-// once per non-zero (ncu r1b: 13.8 GB → 5.1 GB, L2 hit rate 10 % → 55 %).
-constexpr int SPMM_PW_MAX = 16;                 // warps per CTA (fewer when d is large)
-constexpr int SPMM_LIST = 128;                  // flattened entries per warp per round
-constexpr int SPMM_ITEM_SHIFT = 27;             // column < 2^27, item (0..31) above it
-constexpr int SPMM_PSEG = 64;                   // non-zeros per row segment in this kernel
-constexpr int SPMM_WINDOW = 2;                  // panels a CTA may run ahead of the slowest one
-constexpr int SPMM_GIF = 16;                    // gathers in flight per warp
+// re-fetches every gathered row from DRAM (ncu r1b: 13.8 GB of traffic for 1.4 GB of compulsory
+// bytes, L2 hit rate 10 %).  Here the columns are cut into panels whose B rows fit the L2 and the
+// product is taken one panel per LAUNCH: stream order is the only synchronisation, every launch
+// gathers from one L2-resident slice of B, and the per-segment partial sums travel through global
+// memory between launches (read-modify-write of one accumulator row per non-empty piece, skipped
+// for empty pieces, plain write for the first piece).  CSR rows are column-sorted, so the piece of
+// a row segment that falls into a panel is a contiguous run; its bounds come from one streaming
+// pass over the indices (k_pan_offsets).  A warp owns PAN_SLOTS segments per launch:
+// the eight pieces are flattened into one entry list (lane ↔ entry) so that the gathers of short
+// pieces are issued back to back, and the eight accumulator rows sit in shared memory.  The
+// additions into one accumulator happen in ascending column order — the plain kernel's order — so
+// the two kernels agree bit for bit.
+//
+// Measured on C5 (profiles/r1c_*): the panels do cut DRAM traffic (13.9 GB → ~7 GB) but the graph's
+// rows are short (median 48 non-zeros), so a piece is a handful of non-zeros and the per-piece
+// accumulator round trip plus the extra launches cost more than the saved gathers: 3.1 ms at best
+// against 2.54 ms for the plain kernel, which already streams its traffic at 84 % of the DRAM copy peak.
+// The path is therefore opt-in (LT_SPMM_PANEL=1; LT_SPMM_PANEL_MB / LT_SPMM_PANEL_LMIN tune it) and
+// kept for graphs with long rows; the parity test covers it.
+constexpr int PAN_SLOTS = 8;                    // row segments per warp
+constexpr int PAN_THREADS = 256;                // 8 warps per CTA
+constexpr int PAN_GIF = 8;                      // gathers in flight per lane
+constexpr uint32_t PAN_FIRST = 0x80000000u;     // offset flag: nothing of the segment lies before it
 
-__global__ void __launch_bounds__(SPMM_PW_MAX * 32, 1)
-k_spmm_panel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices, const float* __restrict__ values,
-             const int32_t* __restrict__ rows, int32_t n_rows, const int32_t* __restrict__ seg_off,
-             const float4* __restrict__ B4, int64_t ldb4, int32_t d4, const float* __restrict__ bias, int relu,
-             float* __restrict__ C, int64_t ldc, float* __restrict__ partial, int32_t n_cols, int32_t panel_w,
-             int32_t n_panels, int* __restrict__ progress) {
-    extern __shared__ __align__(16) float smem_f[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    const int items_cta = nw * 32;
-    const int32_t total = seg_off[n_rows];
-    const int d = d4 * 4;
-    float4* my_acc = reinterpret_cast<float4*>(smem_f + (size_t)warp * 32 * d);           // this warp's 32 rows
-    uint2* my_list = reinterpret_cast<uint2*>(smem_f + (size_t)nw * 32 * d) + warp * SPMM_LIST;
-    const int n_batches = (total + items_cta - 1) / items_cta;
+// seg_row[g] = position (in the row list) of the row that owns segment g
+__global__ void k_pan_segrow(const int32_t* __restrict__ seg_off, int32_t n_rows, int32_t* __restrict__ seg_row) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_rows) return;
+    for (int32_t g = seg_off[i]; g < seg_off[i + 1]; ++g) seg_row[g] = (int32_t)i;
+}
 
-    int done = 0;                                // panel phases this CTA has completed
-    for (int batch = blockIdx.x; batch < n_batches; batch += gridDim.x) {
-        // ---- lane ↔ one row segment; segment g of the global list goes to batch g % n_batches
-        const int32_t g = (warp * 32 + lane) * n_batches + batch;
-        int32_t i = 0, nseg = 0, cur = 0, s1 = 0;
-        if (g < total) {
-            i = (int32_t)upper_bound(seg_off, 0, (int64_t)n_rows + 1, g) - 1;
-            const int32_t r = rows ? rows[i] : i;
-            const int32_t first = seg_off[i];
-            nseg = seg_off[i + 1] - first;
-            cur = indptr[r] + (g - first) * SPMM_PSEG;
-            s1 = min(indptr[r + 1], cur + SPMM_PSEG);
+// One warp per segment: poff[q][g] = first entry of segment g whose column is in panel ≥ q (q = 0..P),
+// flagged PAN_FIRST when it is the segment's first entry; seg_dst[g] = float offset of its accumulator
+// row (≥ 0: row of C, single-segment rows; < 0: ~offset into `partial`).  Empty rows get their result here.
+__global__ void __launch_bounds__(256)
+k_pan_offsets(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices, const int32_t* __restrict__ rows,
+              const int32_t* __restrict__ sel, const int32_t* __restrict__ seg_off, const int32_t* __restrict__ seg_row, int32_t total_seg, int32_t seg_len,
+              int32_t panel_w, int32_t n_panels, int32_t d, int64_t ldc, const float* __restrict__ bias, int relu,
+              uint32_t* __restrict__ poff, int64_t* __restrict__ seg_dst, float* __restrict__ C) {
+    const int lane = threadIdx.x & 31;
+    const int64_t g = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (g >= total_seg) return;
+    const int32_t i = seg_row[g];
+    const int32_t il = list_pos(sel, i);
+    const int32_t r = rows ? rows[il] : il;
+    const int32_t first = seg_off[i], nseg = seg_off[i + 1] - first;
+    const int32_t s0 = indptr[r] + ((int32_t)g - first) * seg_len;
+    const int32_t s1 = min(indptr[r + 1], s0 + seg_len);
+    if (lane == 0) seg_dst[g] = nseg == 1 ? (int64_t)il * ldc : ~((int64_t)g * d);
+    int32_t carry = -1;                                   // panel of the entry before this chunk
+    for (int32_t base = s0; base < s1; base += 32) {
+        const int32_t k = base + lane;
+        const int32_t q = k < s1 ? indices[k] / panel_w : n_panels;   // past-the-end lanes close all panels
+        int32_t qp = __shfl_up_sync(LT_FULL, q, 1);
+        if (lane == 0) qp = carry;
+        if (k <= s1) {                                    // lane k == s1 writes the tail offsets
+            const uint32_t v = (uint32_t)k | (k == s0 ? PAN_FIRST : 0u);
+            for (int32_t t = qp + 1; t <= q; ++t) poff[(int64_t)t * total_seg + g] = v;
         }
-        for (int k = lane; k < 32 * d4; k += 32) my_acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-        __syncwarp();
-
-        for (int pi = 0; pi < n_panels; ++pi) {
-            // ---- stay within SPMM_WINDOW panels of the slowest CTA
-            if (warp == 0) {
-                const int need = done - SPMM_WINDOW;
-                if (need > 0) {
-                    for (;;) {
-                        int mn = INT32_MAX;
-                        for (int c = lane; c < (int)gridDim.x; c += 32)
-                            mn = min(mn, *reinterpret_cast<volatile int*>(progress + c));
-#pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) mn = min(mn, __shfl_xor_sync(LT_FULL, mn, o));
-                        if (mn >= need) break;
-                    }
-                }
-            }
-            __syncthreads();
-            const bool last_panel = pi == n_panels - 1;
-            const int32_t lim = last_panel ? INT32_MAX : (pi + 1) * panel_w;
-            // 1. advance this lane's cursor to the end of the panel
-            int32_t nxt = cur;
-            if (last_panel) {
-                nxt = s1;
-            } else {
-                int probes = 0;
-                while (nxt < s1) {
-                    const int32_t w0 = indices[nxt];
-                    const int32_t w1 = nxt + 1 < s1 ? indices[nxt + 1] : INT32_MAX;
-                    const int32_t w2 = nxt + 2 < s1 ? indices[nxt + 2] : INT32_MAX;
-                    const int32_t w3 = nxt + 3 < s1 ? indices[nxt + 3] : INT32_MAX;
-                    const int c = (w0 < lim) + (w1 < lim) + (w2 < lim) + (w3 < lim);
-                    nxt += c;
-                    if (c < 4) break;
-                    if (++probes == 2) {
-                        nxt = (int32_t)lower_bound(indices, (int64_t)nxt, (int64_t)s1, lim);
-                        break;
-                    }
-                }
-            }
-            const int32_t cnt = nxt - cur;
-            // 2. exclusive warp scan of the run lengths
-            int32_t inc = cnt;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int32_t u = __shfl_up_sync(LT_FULL, inc, o);
-                if (lane >= o) inc += u;
-            }
-            const int32_t off = inc - cnt;
-            const int32_t tot = __shfl_sync(LT_FULL, inc, 31);
-            for (int32_t r0 = 0; r0 < tot; r0 += SPMM_LIST) {     // rounds of SPMM_LIST entries
-                const int32_t m = min(SPMM_LIST, tot - r0);
-                for (int32_t t0 = 0; t0 < m; t0 += 32) {
-                    const int32_t slot = r0 + t0 + lane;
-                    int owner = 0;
-#pragma unroll
-                    for (int step = 16; step > 0; step >>= 1) {
-                        const int32_t v = __shfl_sync(LT_FULL, inc, owner + step - 1);
-                        if (v <= slot) owner += step;
-                    }
-                    owner = min(owner, 31);
-                    const int32_t e = __shfl_sync(LT_FULL, cur, owner) + (slot - __shfl_sync(LT_FULL, off, owner));
-                    if (t0 + lane < m)
-                        my_list[t0 + lane] = make_uint2((uint32_t)indices[e] | ((uint32_t)owner << SPMM_ITEM_SHIFT),
-                                                        __float_as_uint(values[e]));
-                }
-                __syncwarp();
-                // 3. cooperative gathers
-                int32_t t = 0;
-                for (; t + SPMM_GIF <= m; t += SPMM_GIF) {
-                    uint2 en[SPMM_GIF];
-                    float4 x[SPMM_GIF];
-#pragma unroll
-                    for (int u = 0; u < SPMM_GIF; ++u) en[u] = my_list[t + u];
-#pragma unroll
-                    for (int u = 0; u < SPMM_GIF; ++u) {
-                        const int64_t col = en[u].x & ((1u << SPMM_ITEM_SHIFT) - 1u);
-                        x[u] = lane < d4 ? __ldg(B4 + col * ldb4 + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
-                    if (lane < d4) {
-#pragma unroll
-                        for (int u = 0; u < SPMM_GIF; ++u) {
-                            float4* p = my_acc + (size_t)(en[u].x >> SPMM_ITEM_SHIFT) * d4 + lane;
-                            float4 a = *p;
-                            fma4(a, __uint_as_float(en[u].y), x[u]);
-                            *p = a;
-                        }
-                    }
-                }
-                for (; t < m; t += 4) {
-                    uint2 en[4];
-                    float4 x[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) en[u] = t + u < m ? my_list[t + u] : make_uint2(0u, 0u);
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int64_t col = en[u].x & ((1u << SPMM_ITEM_SHIFT) - 1u);
-                        x[u] = (lane < d4 && t + u < m) ? __ldg(B4 + col * ldb4 + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
-                    if (lane < d4) {
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            if (t + u < m) {
-                                float4* p = my_acc + (size_t)(en[u].x >> SPMM_ITEM_SHIFT) * d4 + lane;
-                                float4 a = *p;
-                                fma4(a, __uint_as_float(en[u].y), x[u]);
-                                *p = a;
-                            }
-                        }
-                    }
-                }
-                __syncwarp();
-            }
-            cur = nxt;
-            // ---- publish progress (after every warp of the CTA has finished the panel)
-            __syncthreads();
-            ++done;
-            if (threadIdx.x == 0) *reinterpret_cast<volatile int*>(progress + blockIdx.x) = done;
-        }
-        // ---- write the 32 rows out (single-segment rows get bias / ReLU here, the others go to `partial`)
-        for (int l0 = 0; l0 < 32; ++l0) {
-            const int32_t g0 = (warp * 32 + l0) * n_batches + batch;
-            if (g0 >= total) break;
-            const int32_t i0 = __shfl_sync(LT_FULL, i, l0);
-            const int32_t ns0 = __shfl_sync(LT_FULL, nseg, l0);
-            if (lane < d4) {
-                float4 a = my_acc[(size_t)l0 * d4 + lane];
-                if (ns0 == 1) {
-                    if (bias) {
-                        const float4 b = __ldg(reinterpret_cast<const float4*>(bias) + lane);
-                        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
-                    }
-                    if (relu) { a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f); }
-                    reinterpret_cast<float4*>(C + (int64_t)i0 * ldc)[lane] = a;
-                } else {
-                    reinterpret_cast<float4*>(partial)[(int64_t)g0 * d4 + lane] = a;
-                }
-            }
-        }
-        __syncwarp();
+        carry = __shfl_sync(LT_FULL, q, 31);
     }
-    // a CTA that has run out of batches must not hold the others back
-    __syncthreads();
-    if (threadIdx.x == 0) *reinterpret_cast<volatile int*>(progress + blockIdx.x) = INT32_MAX;
+    if (carry < n_panels) {                               // segment length a multiple of 32 (or empty): tail offsets
+        const uint32_t v = (uint32_t)s1 | (s1 == s0 ? PAN_FIRST : 0u);
+        for (int32_t t = carry + 1 + lane; t <= n_panels; t += 32) poff[(int64_t)t * total_seg + g] = v;
+    }
+    if (s0 == s1 && nseg == 1)                            // empty row: no piece will ever write it
+        for (int col = lane; col < d; col += 32) {
+            float a = bias ? bias[col] : 0.f;
+            if (relu) a = fmaxf(a, 0.f);
+            C[(int64_t)il * ldc + col] = a;
+        }
+}
+
+__global__ void __launch_bounds__(PAN_THREADS)
+k_spmm_pan(const int32_t* __restrict__ indices, const float* __restrict__ values, const uint32_t* __restrict__ poff_lo,
+           const uint32_t* __restrict__ poff_hi, int32_t total_seg, const int64_t* __restrict__ seg_dst,
+           const float4* __restrict__ B4, int64_t ldb4, int32_t d4, float* C, float* partial) {
+    __shared__ float4 acc_s[PAN_THREADS / 32][PAN_SLOTS][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // segments are dealt round-robin (slot sl of warp w is segment w + sl·W): the consecutive full
+    // segments of a hub row, which all fall into one or two panels, end up in different warps
+    const int64_t W = ((int64_t)total_seg + PAN_SLOTS - 1) / PAN_SLOTS;
+    const int64_t w = (int64_t)blockIdx.x * (PAN_THREADS / 32) + warp;
+    if (w >= W) return;
+    int32_t a = 0, cnt = 0;
+    int first = 1;
+    int64_t dst = 0;
+    const int64_t gl = w + (int64_t)lane * W;
+    if (lane < PAN_SLOTS && gl < total_seg) {
+        const uint32_t ra = poff_lo[gl];
+        const uint32_t rb = poff_hi[gl];
+        dst = seg_dst[gl];
+        a = (int32_t)(ra & ~PAN_FIRST);
+        first = (int)(ra >> 31);
+        cnt = (int32_t)(rb & ~PAN_FIRST) - a;
+    }
+    const int32_t incl = warp_inclusive_scan(cnt);
+    const int32_t total = __shfl_sync(LT_FULL, incl, 31);
+    if (total == 0) return;
+
+    // accumulator rows of the non-empty pieces: asynchronous global → shared copies (no registers held),
+    // waited for after the first index loads have been issued
+#pragma unroll
+    for (int sl = 0; sl < PAN_SLOTS; ++sl) {
+        const int32_t c_s = __shfl_sync(LT_FULL, cnt, sl);
+        const int fs = __shfl_sync(LT_FULL, first, sl);
+        const int64_t ds = __shfl_sync(LT_FULL, dst, sl);
+        if (c_s > 0 && lane < d4) {
+            if (fs) {
+                acc_s[warp][sl][lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+            } else {
+                const float4* src = reinterpret_cast<const float4*>(ds >= 0 ? C + ds : partial + ~ds) + lane;
+                const uint32_t sm = (uint32_t)__cvta_generic_to_shared(&acc_s[warp][sl][lane]);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sm), "l"(src) : "memory");
+            }
+        }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    bool staged = false;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);       // the one open accumulator row (slots are visited in order)
+    for (int32_t base = 0; base < total; base += 32) {
+        // lane ↔ entry base+lane of the flattened list: its slot and position in the CSR arrays
+        const int32_t q = base + lane;
+        int slot = 0;
+#pragma unroll
+        for (int sl = 0; sl < PAN_SLOTS - 1; ++sl) slot += (__shfl_sync(LT_FULL, incl, sl) <= q) ? 1 : 0;
+        const int32_t in_q = __shfl_sync(LT_FULL, incl, slot), cn_q = __shfl_sync(LT_FULL, cnt, slot);
+        const int32_t a_q = __shfl_sync(LT_FULL, a, slot);
+        const int32_t pos = a_q + (q - (in_q - cn_q));
+        // float4 index of the gathered row's first element (32 bits: B up to 64 GB), so that a gather costs
+        // one shuffle, one wide multiply-add and the load
+        const uint32_t mo = q < total ? (uint32_t)indices[pos] * (uint32_t)ldb4 : 0u;
+        const float mv = q < total ? values[pos] : 0.f;
+        const uint32_t starts = __ballot_sync(LT_FULL, q < total && q == in_q - cn_q);   // entry opens its slot's run
+        const uint32_t ends = __ballot_sync(LT_FULL, q < total && q == in_q - 1);        // entry closes it
+        if (!staged) {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            staged = true;
+            __syncwarp();
+        }
+        const int m = min(32, total - base);
+        const float4* Bl = B4 + min(lane, d4 - 1);        // unconditional loads (see k_spmm_vec)
+        for (int k = 0; k < m; k += PAN_GIF) {
+            float4 x[PAN_GIF];
+#pragma unroll
+            for (int u = 0; u < PAN_GIF; ++u)            // unconditional; entries past m carry offset 0
+                x[u] = __ldg(Bl + __shfl_sync(LT_FULL, mo, k + u));
+#pragma unroll
+            for (int u = 0; u < PAN_GIF; ++u) {
+                const float v = __shfl_sync(LT_FULL, mv, k + u);
+                if (k + u >= m) break;                    // warp-uniform
+                if ((starts >> (k + u)) & 1u)             // warp-uniform: zero or the staged partial sum
+                    acc = acc_s[warp][__shfl_sync(LT_FULL, slot, k + u)][lane];
+                fma4(acc, v, x[u]);
+                if ((ends >> (k + u)) & 1u) {             // warp-uniform: the row goes back to global memory
+                    const int64_t ds = __shfl_sync(LT_FULL, dst, __shfl_sync(LT_FULL, slot, k + u));
+                    if (lane < d4) reinterpret_cast<float4*>(ds >= 0 ? C + ds : partial + ~ds)[lane] = acc;
+                }
+            }
+        }
+    }
+}
+
+// bias / ReLU on the single-segment rows after the last panel (multi-segment rows: k_spmm_fixup)
+__global__ void k_pan_epilogue(const int32_t* __restrict__ seg_off, const int32_t* __restrict__ sel, int32_t n_rows, int32_t d,
+                               const float* __restrict__ bias, int relu, float* __restrict__ C, int64_t ldc) {
+    const int lane = threadIdx.x & 31;
+    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (i >= n_rows || seg_off[i + 1] - seg_off[i] != 1) return;
+    const int64_t il = list_pos(sel, i);
+    for (int col = lane; col < d; col += 32) {
+        float a = C[il * ldc + col];
+        if (bias) a += bias[col];
+        if (relu) a = fmaxf(a, 0.f);
+        C[il * ldc + col] = a;
+    }
+}
+
+// split a row list by row length: long rows (≥ lmin non-zeros) take the panel path
+__global__ void k_pan_classify(const int32_t* __restrict__ indptr, const int32_t* __restrict__ rows, int32_t n_rows,
+                               int32_t lmin, int32_t* __restrict__ flag) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_rows) return;
+    const int32_t r = rows ? rows[t] : (int32_t)t;
+    flag[t] = (indptr[r + 1] - indptr[r] >= lmin) ? 1 : 0;
+}
+// pos = exclusive scan of flag: long rows → sel_long[pos], short rows → sel_short[t - pos]; counts[0..1] = {long, short}
+__global__ void k_pan_split(const int32_t* __restrict__ flag, const int32_t* __restrict__ pos, int32_t n_rows,
+                            int32_t* __restrict__ sel_long, int32_t* __restrict__ sel_short, int32_t* __restrict__ counts) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_rows) return;
+    if (flag[t]) sel_long[pos[t]] = (int32_t)t; else sel_short[t - pos[t]] = (int32_t)t;
+    if (t == 0) { counts[0] = pos[n_rows]; counts[1] = n_rows - pos[n_rows]; }
 }
 
 // Generic fallback (d not a multiple of 4, unaligned, or d > 512): one warp per row, lanes are split
@@ -363,7 +375,7 @@ int spmm_csr_f32(const int32_t* indptr, const int32_t* indices, const float* val
                  const int32_t* rows, int32_t n_rows, const float* B, int64_t ldb, int32_t d, const float* bias, int relu,
                  float* C, int64_t ldc, cudaStream_t s) {
     if (n_rows == 0 || d == 0) return LT_OK;
-    const bool vec = (d % 4 == 0) && (ldb % 4 == 0) && (ldc % 4 == 0) && d <= 512 &&
+    const bool vec = (d % 4 == 0) && (ldb % 4 == 0) && (ldc % 4 == 0) && d <= 512 && (int64_t)n_cols * (ldb / 4) < ((int64_t)1 << 32) &&
                      ((uintptr_t)B % 16 == 0) && ((uintptr_t)C % 16 == 0) && (!bias || (uintptr_t)bias % 16 == 0);
     if (!vec) {
         const unsigned bl = (unsigned)ceil_div((int64_t)n_rows * 32, SPMM_THREADS);
@@ -378,63 +390,122 @@ int spmm_csr_f32(const int32_t* indptr, const int32_t* indices, const float* val
         LT_LAUNCH_CHECK();
         return LT_OK;
     }
-    // dense operand far beyond the L2 and enough rows to fill the machine: panel-blocked kernel
     const int32_t d4 = d / 4;
+    const float4* B4 = reinterpret_cast<const float4*>(B);
+    Scratch scratch(s);
+
+    // the plain pass over a row list (sel == null: the whole list); total_seg < 0: not known yet (one 4-byte sync)
+    auto plain_pass = [&](const int32_t* sel, int32_t n_list, int32_t* seg_off, int64_t total_seg) -> int {
+        if (n_list == 0) return LT_OK;
+        if (total_seg < 0) {
+            k_spmm_segcount<<<(unsigned)ceil_div(n_list, 256), 256, 0, s>>>(indptr, rows, sel, nullptr, n_list, SPMM_SEG, seg_off);
+            LT_LAUNCH_CHECK();
+            LT_TRY(exclusive_scan_i32(seg_off, seg_off, n_list, s));
+            // the number of segments sizes the grid and the partial-sum buffer: 4-byte copy, one sync per SpMM
+            int32_t h = 0;
+            LT_CUDA(cudaMemcpyAsync(&h, seg_off + n_list, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+            LT_CUDA(cudaStreamSynchronize(s));
+            total_seg = h;
+        }
+        float* partial = nullptr;
+        const bool multi = total_seg > n_list;
+        if (multi) LT_TRY(scratch.alloc(&partial, (size_t)total_seg * d));
+        const unsigned bl = (unsigned)ceil_div(total_seg * 32, SPMM_THREADS);
+#define LT_SPMM_V(NV_, GIF_, MINB_) k_spmm_vec<NV_, GIF_, MINB_><<<bl, SPMM_THREADS, 0, s>>>(indptr, indices, values, rows, sel, n_list, seg_off, B4, (uint32_t)(ldb / 4), d4, bias, relu, C, ldc, partial)
+        // d ≤ 128: 8 gathers in flight per lane at 3 CTAs/SM (no spills) measured best on C5 (2.54 ms; 4 CTAs 2.64,
+        // 16 in flight at 2 CTAs 3.16): the kernel then moves its 13.9 GB of DRAM traffic at 84 % of the copy peak
+        if (d4 <= 32) LT_SPMM_V(1, 8, 3);
+        else if (d4 <= 64) LT_SPMM_V(2, 4, 4);
+        else if (d4 <= 96) LT_SPMM_V(3, 4, 3);
+        else LT_SPMM_V(4, 4, 2);
+#undef LT_SPMM_V
+        LT_LAUNCH_CHECK();
+        if (multi) {
+            k_spmm_fixup<<<(unsigned)ceil_div((int64_t)n_list * 32, 256), 256, 0, s>>>(seg_off, sel, n_list, partial, d, bias,
+                                                                                     relu, C, ldc);
+            LT_LAUNCH_CHECK();
+        }
+        return LT_OK;
+    };
+
+    // dense operand far beyond the L2 and enough rows to amortise the extra launches: long rows go through
+    // one launch per column panel, short rows (a piece per panel would be a couple of non-zeros) stay plain
     const int64_t b_bytes = (int64_t)n_cols * d * 4;
     const char* pm = getenv("LT_SPMM_PANEL_MB");
-    const int64_t panel_bytes = (int64_t)(pm ? atoi(pm) : 32) << 20;
-    int nw = (int)((232448 - 1024) / (32 * (size_t)d * 4 + SPMM_LIST * 8));
-    if (nw > SPMM_PW_MAX) nw = SPMM_PW_MAX;
-    const bool use_panel = d4 <= 32 && nw >= 4 && n_cols < (1 << SPMM_ITEM_SHIFT) && b_bytes >= ((int64_t)256 << 20) &&
-                           n_rows >= 64 * 512 && getenv("LT_SPMM_PANEL") && !getenv("LT_SPMM_NO_PANEL");
-    Scratch scratch(s);
-    int32_t* seg_off;
-    LT_TRY(scratch.alloc(&seg_off, (size_t)n_rows + 1));
-    k_spmm_segcount<<<(unsigned)ceil_div(n_rows, 256), 256, 0, s>>>(indptr, rows, n_rows, use_panel ? SPMM_PSEG : SPMM_SEG,
-                                                                   seg_off);
+    const char* pl = getenv("LT_SPMM_PANEL_LMIN");
+    const int64_t panel_bytes = (int64_t)(pm ? atoi(pm) : 48) << 20;
+    const int32_t lmin = pl ? atoi(pl) : 64;
+    const bool use_panel = d4 <= 32 && b_bytes >= ((int64_t)256 << 20) && n_rows >= 32768 && getenv("LT_SPMM_PANEL");
+    if (!use_panel) {
+        int32_t* seg_off;
+        LT_TRY(scratch.alloc(&seg_off, (size_t)n_rows + 1));
+        return plain_pass(nullptr, n_rows, seg_off, -1);
+    }
+    int32_t *flag, *pos, *sel_long, *sel_short, *counts, *off_long, *off_short;
+    LT_TRY(scratch.alloc(&flag, (size_t)n_rows + 1));
+    LT_TRY(scratch.alloc(&pos, (size_t)n_rows + 1));
+    LT_TRY(scratch.alloc(&sel_long, (size_t)n_rows));
+    LT_TRY(scratch.alloc(&sel_short, (size_t)n_rows));
+    LT_TRY(scratch.alloc(&counts, 2));
+    LT_TRY(scratch.alloc(&off_long, (size_t)n_rows + 1));
+    LT_TRY(scratch.alloc(&off_short, (size_t)n_rows + 1));
+    const unsigned blr = (unsigned)ceil_div(n_rows, 256);
+    k_pan_classify<<<blr, 256, 0, s>>>(indptr, rows, n_rows, lmin, flag);
     LT_LAUNCH_CHECK();
-    LT_TRY(exclusive_scan_i32(seg_off, seg_off, n_rows, s));
-    // the number of segments sizes the grid and the partial-sum buffer: 4-byte copy, one sync per SpMM
-    int32_t nnz_bound = 0;
-    LT_CUDA(cudaMemcpyAsync(&nnz_bound, seg_off + n_rows, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    LT_TRY(exclusive_scan_i32(flag, pos, n_rows, s));
+    k_pan_split<<<blr, 256, 0, s>>>(flag, pos, n_rows, sel_long, sel_short, counts);
+    LT_LAUNCH_CHECK();
+    k_spmm_segcount<<<blr, 256, 0, s>>>(indptr, rows, sel_long, counts, n_rows, SPMM_SEG, off_long);
+    LT_LAUNCH_CHECK();
+    k_spmm_segcount<<<blr, 256, 0, s>>>(indptr, rows, sel_short, counts + 1, n_rows, SPMM_SEG, off_short);
+    LT_LAUNCH_CHECK();
+    LT_TRY(exclusive_scan_i32(off_long, off_long, n_rows, s));
+    LT_TRY(exclusive_scan_i32(off_short, off_short, n_rows, s));
+    int32_t hc[4] = {0, 0, 0, 0};   // long rows, short rows, long segments, short segments: one sync per SpMM
+    LT_CUDA(cudaMemcpyAsync(&hc[0], counts, 8, cudaMemcpyDeviceToHost, s));
+    LT_CUDA(cudaMemcpyAsync(&hc[2], off_long + n_rows, 4, cudaMemcpyDeviceToHost, s));
+    LT_CUDA(cudaMemcpyAsync(&hc[3], off_short + n_rows, 4, cudaMemcpyDeviceToHost, s));
     LT_CUDA(cudaStreamSynchronize(s));
-    const int64_t total_seg = nnz_bound;
-    float* partial = nullptr;
-    const bool multi = total_seg > n_rows;
-    if (multi) LT_TRY(scratch.alloc(&partial, (size_t)total_seg * d));
-    const float4* B4 = reinterpret_cast<const float4*>(B);
-    if (use_panel) {
+    const int32_t n_long = hc[0], n_short = hc[1];
+    const int64_t total_seg = hc[2];
+    LT_TRY(plain_pass(sel_short, n_short, off_short, hc[3]));
+    if (n_long == 0) return LT_OK;
+    {
+        float* partial = nullptr;
+        const bool multi = total_seg > n_long;
+        if (multi) LT_TRY(scratch.alloc(&partial, (size_t)total_seg * d));
         int32_t n_panels = (int32_t)ceil_div(b_bytes, panel_bytes);
         const int32_t panel_w = (int32_t)ceil_div(n_cols, n_panels);
         n_panels = (int32_t)ceil_div(n_cols, panel_w);
-        const size_t smem = (size_t)nw * (32 * (size_t)d * 4 + SPMM_LIST * 8);
-        LT_CUDA(cudaFuncSetAttribute(k_spmm_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        const unsigned grid = (unsigned)min((int64_t)num_sms(), ceil_div(total_seg, nw * 32));
-        int* progress;
-        LT_TRY(scratch.alloc(&progress, (size_t)grid));
-        LT_CUDA(cudaMemsetAsync(progress, 0, sizeof(int) * grid, s));
-        const int64_t ldb4 = ldb / 4;
-        void* args[] = {(void*)&indptr, (void*)&indices, (void*)&values, (void*)&rows, (void*)&n_rows, (void*)&seg_off,
-                        (void*)&B4, (void*)&ldb4, (void*)&d4, (void*)&bias, (void*)&relu, (void*)&C, (void*)&ldc,
-                        (void*)&partial, (void*)&n_cols, (void*)&panel_w, (void*)&n_panels, (void*)&progress};
-        LT_CUDA(cudaLaunchCooperativeKernel((const void*)k_spmm_panel, dim3(grid), dim3(nw * 32), args, smem, s));
+        int32_t* seg_row;
+        uint32_t* poff;
+        int64_t* seg_dst;
+        LT_TRY(scratch.alloc(&seg_row, (size_t)total_seg));
+        LT_TRY(scratch.alloc(&poff, (size_t)(n_panels + 1) * total_seg));
+        LT_TRY(scratch.alloc(&seg_dst, (size_t)total_seg));
+        k_pan_segrow<<<(unsigned)ceil_div(n_long, 256), 256, 0, s>>>(off_long, n_long, seg_row);
         LT_LAUNCH_CHECK();
-    } else {
-        const unsigned bl = (unsigned)ceil_div(total_seg * 32, SPMM_THREADS);
-#define LT_SPMM_V(NV_, GIF_) k_spmm_vec<NV_, GIF_><<<bl, SPMM_THREADS, 0, s>>>(indptr, indices, values, rows, n_rows, seg_off, B4, ldb / 4, d4, bias, relu, C, ldc, partial)
-        const char* gf = getenv("LT_SPMM_GIF");
-        const int gif = gf ? atoi(gf) : 8;
-        if (d4 <= 32) { if (gif >= 16) LT_SPMM_V(1, 16); else if (gif >= 8) LT_SPMM_V(1, 8); else LT_SPMM_V(1, 4); }
-        else if (d4 <= 64) LT_SPMM_V(2, 4);
-        else if (d4 <= 96) LT_SPMM_V(3, 4);
-        else LT_SPMM_V(4, 4);
-#undef LT_SPMM_V
+        k_pan_offsets<<<(unsigned)ceil_div(total_seg * 32, 256), 256, 0, s>>>(indptr, indices, rows, sel_long, off_long, seg_row,
+                                                                            (int32_t)total_seg, SPMM_SEG, panel_w, n_panels,
+                                                                            d, ldc, bias, relu, poff, seg_dst, C);
         LT_LAUNCH_CHECK();
-    }
-    if (multi) {
-        k_spmm_fixup<<<(unsigned)ceil_div((int64_t)n_rows * 32, 256), 256, 0, s>>>(seg_off, n_rows, partial, d, bias,
-                                                                                 relu, C, ldc);
-        LT_LAUNCH_CHECK();
+        const unsigned bl = (unsigned)ceil_div(total_seg, (PAN_THREADS / 32) * PAN_SLOTS);
+        for (int32_t p = 0; p < n_panels; ++p) {
+            k_spmm_pan<<<bl, PAN_THREADS, 0, s>>>(indices, values, poff + (int64_t)p * total_seg,
+                                                  poff + (int64_t)(p + 1) * total_seg, (int32_t)total_seg, seg_dst, B4,
+                                                  ldb / 4, d4, C, partial);
+            LT_LAUNCH_CHECK();
+        }
+        if (bias || relu) {
+            k_pan_epilogue<<<(unsigned)ceil_div((int64_t)n_long * 32, 256), 256, 0, s>>>(off_long, sel_long, n_long, d, bias,
+                                                                                       relu, C, ldc);
+            LT_LAUNCH_CHECK();
+        }
+        if (multi) {
+            k_spmm_fixup<<<(unsigned)ceil_div((int64_t)n_long * 32, 256), 256, 0, s>>>(off_long, sel_long, n_long, partial, d,
+                                                                                     bias, relu, C, ldc);
+            LT_LAUNCH_CHECK();
+        }
     }
     return LT_OK;
 }

@@ -1,6 +1,7 @@
-"""Panel-blocked SpMM (k_spmm_panel) vs the plain kernel and a float64 product, on a graph whose dense
-operand exceeds the L2 (the regime it is selected for), including hub rows split into segments and a
-row subset."""
+"""Panel-blocked SpMM (k_spmm_pan, one launch per column panel) vs the plain kernel and a float64
+product, on a graph whose dense operand exceeds the L2 (the regime it is selected for), including hub
+rows split into segments, a row subset, and several panel widths.  Both kernels add the terms of a
+row in ascending column order, so they must agree bit for bit."""
 import os
 
 import numpy as np
@@ -23,21 +24,26 @@ def test_spmm_panel_matches_plain_and_float64():
     rows = torch.randperm(n, generator=g, device="cuda")[:200_000].sort().values.int()
     deg = (hat.indptr[1:] - hat.indptr[:-1]).max().item()
     assert deg > 256                             # hub rows span several segments
-    os.environ["LT_SPMM_PANEL"] = "1"          # the panel-blocked kernel is opt-in
+    out0 = ops.spmm(hat, b, bias=bias, relu=True)     # plain kernel (default)
+    sub0 = ops.spmm(hat, b, rows=rows)
+    os.environ["LT_SPMM_PANEL"] = "1"                # the panel path is opt-in
     try:
         out = ops.spmm(hat, b, bias=bias, relu=True)
         sub = ops.spmm(hat, b, rows=rows)
+        for mb, lmin in (("16", "1"), ("100", "64"), ("48", "300")):
+            os.environ["LT_SPMM_PANEL_MB"], os.environ["LT_SPMM_PANEL_LMIN"] = mb, lmin
+            try:
+                assert torch.equal(ops.spmm(hat, b, rows=rows), sub0)
+            finally:
+                del os.environ["LT_SPMM_PANEL_MB"], os.environ["LT_SPMM_PANEL_LMIN"]
     finally:
         del os.environ["LT_SPMM_PANEL"]
-    out0 = ops.spmm(hat, b, bias=bias, relu=True)
-    sub0 = ops.spmm(hat, b, rows=rows)
     # float64 check through torch's CSR product
     A = torch.sparse_csr_tensor(hat.indptr.long(), hat.indices.long(), hat.values.double(), (n, n))
     ref = torch.relu(A @ b.double() + bias.double())
     scale = ref.abs().max().item()
     assert (out.double() - ref).abs().max().item() <= 2e-6 * max(scale, 1.0) * 4     # fp32 sums of ≤ ~1e4 terms
     assert (out0.double() - ref).abs().max().item() <= 2e-6 * max(scale, 1.0) * 4
-    # the two kernels associate the per-row sums differently (per-panel partial sums): fp32 rounding apart
-    assert (out - out0).abs().max().item() <= 2e-6 * max(scale, 1.0) * 4
-    assert (sub - sub0).abs().max().item() <= 2e-6 * max(scale, 1.0) * 4
+    assert torch.equal(out, out0)
+    assert torch.equal(sub, sub0)
     assert torch.equal(sub0, ops.spmm(hat, b)[rows.long()])       # a row subset reproduces the full run exactly
