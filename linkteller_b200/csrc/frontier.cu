@@ -70,23 +70,24 @@ __global__ void k_tmap(const int32_t* __restrict__ test_nodes, int32_t T, int32_
 
 // len[i] = nnz of row test_nodes[i] for all T; slice lens go to s_len
 __global__ void k_test_lens(const int32_t* __restrict__ indptr, const int32_t* __restrict__ test_nodes, int32_t T,
-                            int32_t lo, int32_t hi, int32_t* __restrict__ all_len, int32_t* __restrict__ s_len) {
+                            int32_t n, int32_t lo, int32_t hi, int32_t* __restrict__ all_len, int32_t* __restrict__ s_len) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= T) return;
     const int32_t v = test_nodes[i];
-    const int32_t len = indptr[v + 1] - indptr[v];
+    const int32_t len = (v >= 0 && v < n) ? indptr[v + 1] - indptr[v] : 0;   // invalid nodes are reported by k_tmap
     all_len[i] = len;
     if (i >= lo && i < hi) s_len[i - lo] = len;
 }
 
 // one warp per slice row: flag[r] = 1 for every r in row v
 __global__ void k_mark_rows(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
-                            const int32_t* __restrict__ test_nodes, int32_t lo, int32_t Ts,
+                            const int32_t* __restrict__ test_nodes, int32_t n, int32_t lo, int32_t Ts,
                             int32_t* __restrict__ flag) {
     const int lane = threadIdx.x & 31;
     const int64_t j = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (j >= Ts) return;
     const int32_t v = test_nodes[lo + j];
+    if (v < 0 || v >= n) return;
     for (int32_t k = indptr[v] + lane; k < indptr[v + 1]; k += 32) flag[indices[k]] = 1;
 }
 
@@ -130,26 +131,26 @@ __global__ void k_fill_S(const int32_t* __restrict__ indptr, const int32_t* __re
     s_a[e] = a;
 }
 
-// observers: one warp per test node i (all T).  MODE 0 counts per frontier row, MODE 1 fills.
+// observers: one thread per entry of the concatenated rows of all T test nodes (all_off = exclusive
+// scan of their lengths), so a hub test node does not serialise its whole row in one warp.
+// MODE 0 counts per frontier row, MODE 1 fills.
 template <int MODE>
 __global__ void k_observers(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
                             const float* __restrict__ values, const int32_t* __restrict__ test_nodes, int32_t T,
-                            const int32_t* __restrict__ rmap, int32_t* __restrict__ cnt_or_cursor,
-                            int32_t* __restrict__ b_i, float* __restrict__ b_w) {
-    const int lane = threadIdx.x & 31;
-    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (i >= T) return;
-    const int32_t u = test_nodes[i];
-    for (int32_t k = indptr[u] + lane; k < indptr[u + 1]; k += 32) {
-        const int32_t rho = rmap[indices[k]];
-        if (rho < 0) continue;
-        if (MODE == 0) {
-            atomicAdd(&cnt_or_cursor[rho], 1);
-        } else {
-            const int32_t p = atomicAdd(&cnt_or_cursor[rho], 1);
-            b_i[p] = (int32_t)i;
-            b_w[p] = values[k];
-        }
+                            const int32_t* __restrict__ all_off, const int32_t* __restrict__ rmap,
+                            int32_t* __restrict__ cnt_or_cursor, int32_t* __restrict__ b_i, float* __restrict__ b_w) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= all_off[T]) return;
+    const int32_t i = (int32_t)upper_bound(all_off, 0, (int64_t)T + 1, (int32_t)t) - 1;
+    const int32_t k = indptr[test_nodes[i]] + ((int32_t)t - all_off[i]);
+    const int32_t rho = rmap[indices[k]];
+    if (rho < 0) return;
+    if (MODE == 0) {
+        atomicAdd(&cnt_or_cursor[rho], 1);
+    } else {
+        const int32_t p = atomicAdd(&cnt_or_cursor[rho], 1);
+        b_i[p] = i;
+        b_w[p] = values[k];
     }
 }
 
@@ -161,19 +162,19 @@ __global__ void k_rec_counts(const int32_t* __restrict__ s_rho, int64_t E, const
     rc[e] = b_indptr[rho + 1] - b_indptr[rho];
 }
 
-// one warp per incidence: emit its records
+// one thread per incidence: emit its records (a frontier row has a handful of observers; a warp per
+// incidence left most lanes idle)
 __global__ void k_expand(const int32_t* __restrict__ s_j, const int32_t* __restrict__ s_rho, int64_t E,
                          const int32_t* __restrict__ b_indptr, const int32_t* __restrict__ b_i,
                          const float* __restrict__ b_w, const int64_t* __restrict__ rec_off,
                          uint64_t* __restrict__ key, uint64_t* __restrict__ val) {
-    const int lane = threadIdx.x & 31;
-    const int64_t e = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= E) return;
     const int32_t rho = s_rho[e];
     const int32_t b0 = b_indptr[rho], nb = b_indptr[rho + 1] - b0;
     const int64_t dst = rec_off[e];
     const uint64_t jhi = (uint64_t)(uint32_t)s_j[e] << 32, ehi = (uint64_t)(uint32_t)e << 32;
-    for (int32_t k = lane; k < nb; k += 32) {
+    for (int32_t k = 0; k < nb; ++k) {
         key[dst + k] = jhi | (uint32_t)b_i[b0 + k];
         val[dst + k] = ehi | (uint64_t)__float_as_uint(b_w[b0 + k]);
     }
@@ -446,16 +447,12 @@ static int plan_build(lt_plan* p, const int32_t* indptr, const int32_t* indices,
     LT_CUDA(cudaMemsetAsync(err, 0, sizeof(int), s));
     k_tmap<<<(unsigned)ceil_div(T, 256), 256, 0, s>>>(test_nodes, T, n, tmap, err);
     LT_LAUNCH_CHECK();
-    int herr = 0;
-    LT_CUDA(cudaMemcpyAsync(&herr, err, sizeof(int), cudaMemcpyDeviceToHost, s));
-    LT_CUDA(cudaStreamSynchronize(s));   // test nodes must be valid before they index indptr
-    if (herr & 1) { set_error("lt_plan_create: test node outside [0,%d)", n); return LT_ERR_DATA; }
-    if (herr & 2) { set_error("lt_plan_create: duplicate test node"); return LT_ERR_DATA; }
-    k_test_lens<<<(unsigned)ceil_div(T, 256), 256, 0, s>>>(indptr, test_nodes, T, lo, p->hi, all_len, p->s_indptr);
+    int herr = 0;   // read back with the sizes below; until then invalid test nodes are skipped, not dereferenced
+    k_test_lens<<<(unsigned)ceil_div(T, 256), 256, 0, s>>>(indptr, test_nodes, T, n, lo, p->hi, all_len, p->s_indptr);
     LT_LAUNCH_CHECK();
     LT_TRY(exclusive_scan_i32(all_len, all_len, T, s));
     LT_TRY(exclusive_scan_i32(p->s_indptr, p->s_indptr, Ts, s));
-    k_mark_rows<<<(unsigned)ceil_div((int64_t)Ts * 32, 256), 256, 0, s>>>(indptr, indices, test_nodes, lo, Ts, flag);
+    k_mark_rows<<<(unsigned)ceil_div((int64_t)Ts * 32, 256), 256, 0, s>>>(indptr, indices, test_nodes, n, lo, Ts, flag);
     LT_LAUNCH_CHECK();
     int32_t* pos;
     LT_TRY(scratch.alloc(&pos, (size_t)n + 1));
@@ -464,7 +461,10 @@ static int plan_build(lt_plan* p, const int32_t* indptr, const int32_t* indices,
     LT_CUDA(cudaMemcpyAsync(&h3[0], p->s_indptr + Ts, 4, cudaMemcpyDeviceToHost, s));
     LT_CUDA(cudaMemcpyAsync(&h3[1], pos + n, 4, cudaMemcpyDeviceToHost, s));
     LT_CUDA(cudaMemcpyAsync(&h3[2], all_len + T, 4, cudaMemcpyDeviceToHost, s));
+    LT_CUDA(cudaMemcpyAsync(&herr, err, sizeof(int), cudaMemcpyDeviceToHost, s));
     LT_CUDA(cudaStreamSynchronize(s));
+    if (herr & 1) { set_error("lt_plan_create: test node outside [0,%d)", n); return LT_ERR_DATA; }
+    if (herr & 2) { set_error("lt_plan_create: duplicate test node"); return LT_ERR_DATA; }
     p->E = h3[0];
     p->R = h3[1];
     const int64_t nb_cap = h3[2];
@@ -491,12 +491,12 @@ static int plan_build(lt_plan* p, const int32_t* indptr, const int32_t* indices,
     LT_TRY(plan_alloc(p, &p->b_i, (size_t)nb_cap, s));
     LT_TRY(plan_alloc(p, &p->b_w, (size_t)nb_cap, s));
     LT_CUDA(cudaMemsetAsync(p->b_indptr, 0, ((size_t)R + 1) * 4, s));
-    const unsigned blT = (unsigned)ceil_div((int64_t)T * 32, 256);
-    k_observers<0><<<blT, 256, 0, s>>>(indptr, indices, values, test_nodes, T, rmap, p->b_indptr, nullptr, nullptr);
+    const unsigned blT = (unsigned)ceil_div(nb_cap > 0 ? nb_cap : 1, 256);
+    k_observers<0><<<blT, 256, 0, s>>>(indptr, indices, values, test_nodes, T, all_len, rmap, p->b_indptr, nullptr, nullptr);
     LT_LAUNCH_CHECK();
     LT_TRY(exclusive_scan_i32(p->b_indptr, p->b_indptr, R, s));
     LT_CUDA(cudaMemcpyAsync(cursor, p->b_indptr, ((size_t)R + 1) * 4, cudaMemcpyDeviceToDevice, s));
-    k_observers<1><<<blT, 256, 0, s>>>(indptr, indices, values, test_nodes, T, rmap, cursor, p->b_i, p->b_w);
+    k_observers<1><<<blT, 256, 0, s>>>(indptr, indices, values, test_nodes, T, all_len, rmap, cursor, p->b_i, p->b_w);
     LT_LAUNCH_CHECK();
 
     // records
@@ -535,7 +535,7 @@ static int plan_build(lt_plan* p, const int32_t* indptr, const int32_t* indices,
     LT_CUDA(cudaMemsetAsync(p->n_groups, 0, 4, s));
     LT_CUDA(cudaMemsetAsync(p->n_big, 0, 4, s));
     if (M) {
-        k_expand<<<(unsigned)ceil_div(E * 32, 256), 256, 0, s>>>(p->s_j, p->s_rho, E, p->b_indptr, p->b_i, p->b_w,
+        k_expand<<<(unsigned)ceil_div(E, 256), 256, 0, s>>>(p->s_j, p->s_rho, E, p->b_indptr, p->b_i, p->b_w,
                                                                rec_off, p->rec_key, p->rec_val);
         LT_LAUNCH_CHECK();
         BitRange ranges[2] = {{0, bits_for((uint64_t)(T - 1))}, {32, 32 + bits_for((uint64_t)(Ts > 1 ? Ts - 1 : 1))}};

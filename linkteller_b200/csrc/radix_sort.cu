@@ -13,14 +13,15 @@ namespace lt {
 
 constexpr int RS_THREADS = 256;
 constexpr int RS_WARPS = RS_THREADS / 32;
-constexpr int RS_ROUNDS = 16;                          // keys per thread
-constexpr int RS_WARP_KEYS = 32 * RS_ROUNDS;           // 512
-constexpr int RS_TILE = RS_THREADS * RS_ROUNDS;        // 4096
 constexpr int RS_BINS = 256;
+// keys per thread: 16 (tiles of 4096 keys) for large inputs; 4 (tiles of 1024) when 4096-key tiles would
+// leave most SMs without a CTA — the plan's record sort (~10^6 keys) is latency-bound, not bandwidth-bound
 
+template <int RS_ROUNDS>
 __global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const uint64_t* __restrict__ keys, int64_t n,
                                                        int shift, int32_t* __restrict__ counts,
                                                        int32_t n_tiles) {
+    constexpr int RS_TILE = RS_THREADS * RS_ROUNDS;
     __shared__ int32_t hist[RS_BINS];
     hist[threadIdx.x] = 0;
     __syncthreads();
@@ -34,13 +35,15 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const uint64_t* __restri
     counts[(int64_t)threadIdx.x * n_tiles + blockIdx.x] = hist[threadIdx.x];
 }
 
-template <bool HAS_VALS>
+template <bool HAS_VALS, int RS_ROUNDS>
 __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const uint64_t* __restrict__ keys_in,
                                                           const uint64_t* __restrict__ vals_in,
                                                           uint64_t* __restrict__ keys_out,
                                                           uint64_t* __restrict__ vals_out, int64_t n,
                                                           int shift, const int32_t* __restrict__ offsets,
                                                           int32_t n_tiles) {
+    constexpr int RS_WARP_KEYS = 32 * RS_ROUNDS;
+    constexpr int RS_TILE = RS_THREADS * RS_ROUNDS;
     __shared__ int32_t wcnt[RS_WARPS][RS_BINS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int k = threadIdx.x; k < RS_WARPS * RS_BINS; k += RS_THREADS) (&wcnt[0][0])[k] = 0;
@@ -109,7 +112,8 @@ int radix_sort_u64(uint64_t* keys, uint64_t* vals, int64_t n, const BitRange* ra
             shifts[n_pass++] = b;
         }
     if (n_pass == 0) return LT_OK;
-    const int64_t n_tiles = ceil_div(n, RS_TILE);
+    const bool small = ceil_div(n, RS_THREADS * 16) < 4 * (int64_t)num_sms();
+    const int64_t n_tiles = ceil_div(n, RS_THREADS * (small ? 4 : 16));
     Scratch scratch(s);
     uint64_t *k2 = nullptr, *v2 = nullptr;
     int32_t* counts = nullptr;
@@ -117,16 +121,21 @@ int radix_sort_u64(uint64_t* keys, uint64_t* vals, int64_t n, const BitRange* ra
     if (vals) LT_TRY(scratch.alloc(&v2, (size_t)n));
     LT_TRY(scratch.alloc(&counts, (size_t)(RS_BINS * n_tiles + 1)));
     uint64_t *ki = keys, *ko = k2, *vi = vals, *vo = v2;
+    const unsigned g = (unsigned)n_tiles;
+    const int32_t nt = (int32_t)n_tiles;
     for (int p = 0; p < n_pass; ++p) {
-        k_rs_hist<<<(unsigned)n_tiles, RS_THREADS, 0, s>>>(ki, n, shifts[p], counts, (int32_t)n_tiles);
+        const int sh = shifts[p];
+        if (small) k_rs_hist<4><<<g, RS_THREADS, 0, s>>>(ki, n, sh, counts, nt);
+        else k_rs_hist<16><<<g, RS_THREADS, 0, s>>>(ki, n, sh, counts, nt);
         LT_LAUNCH_CHECK();
         LT_TRY(exclusive_scan_i32(counts, counts, RS_BINS * n_tiles, s));
-        if (vals)
-            k_rs_scatter<true><<<(unsigned)n_tiles, RS_THREADS, 0, s>>>(ki, vi, ko, vo, n, shifts[p], counts,
-                                                                        (int32_t)n_tiles);
-        else
-            k_rs_scatter<false><<<(unsigned)n_tiles, RS_THREADS, 0, s>>>(ki, nullptr, ko, nullptr, n, shifts[p],
-                                                                         counts, (int32_t)n_tiles);
+        if (vals) {
+            if (small) k_rs_scatter<true, 4><<<g, RS_THREADS, 0, s>>>(ki, vi, ko, vo, n, sh, counts, nt);
+            else k_rs_scatter<true, 16><<<g, RS_THREADS, 0, s>>>(ki, vi, ko, vo, n, sh, counts, nt);
+        } else {
+            if (small) k_rs_scatter<false, 4><<<g, RS_THREADS, 0, s>>>(ki, nullptr, ko, nullptr, n, sh, counts, nt);
+            else k_rs_scatter<false, 16><<<g, RS_THREADS, 0, s>>>(ki, nullptr, ko, nullptr, n, sh, counts, nt);
+        }
         LT_LAUNCH_CHECK();
         uint64_t* t = ki; ki = ko; ko = t;
         t = vi; vi = vo; vo = t;

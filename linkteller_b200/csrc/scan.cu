@@ -72,14 +72,41 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_down(const TI* in, int64_
     }
 }
 
+// one CTA walks the whole input tile by tile, carrying the running total: one launch instead of three
+// for inputs of a few tiles (the plan has many scans of T-sized arrays)
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_small(const TI* in, int64_t n_in, TO* out, int64_t n_out) {
+    TO carry = 0;
+    for (int64_t tile = 0; tile < n_out; tile += SCAN_TILE) {
+        const int64_t base = tile + (int64_t)threadIdx.x * SCAN_ITEMS;
+        TO v[SCAN_ITEMS];
+        TO s = 0;
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; ++k) {
+            const int64_t i = base + k;
+            v[k] = (i < n_in) ? (TO)in[i] : TO(0);
+            s += v[k];
+        }
+        TO total;
+        TO pre = block_exclusive_scan<TO>(s, total) + carry;
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; ++k) {
+            const int64_t i = base + k;
+            if (i < n_out) out[i] = pre;
+            pre += v[k];
+        }
+        carry += total;
+    }
+}
+
 // Exclusive scan producing n_in+1 outputs (out[n_in] = total).  in may alias out when TI == TO
 // (every tile is fully read into registers before it is written, tiles do not overlap).
 template <typename TI, typename TO>
 static int scan_impl(const TI* in, TO* out, int64_t n_in, cudaStream_t s) {
     const int64_t n_out = n_in + 1;
     const int64_t blocks = ceil_div(n_out, SCAN_TILE);
-    if (blocks == 1) {
-        k_scan_down<TI, TO><<<1, SCAN_THREADS, 0, s>>>(in, n_in, out, n_out, nullptr);
+    if (blocks <= 16) {
+        k_scan_small<TI, TO><<<1, SCAN_THREADS, 0, s>>>(in, n_in, out, n_out);
         LT_LAUNCH_CHECK();
         return LT_OK;
     }
