@@ -124,6 +124,7 @@ k_gemm_tc(Prod prod, const uint32_t* __restrict__ Bimg, const float* __restrict_
     __shared__ uint32_t tmem_base_s;
     __shared__ int64_t meta0[2][TC_BM], meta1[2][TC_BM];
     __shared__ float meta2[2][TC_BM];
+    __shared__ __align__(16) float bias_s[NT];               // this CTA's slice of the bias row (zeros without bias)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
@@ -136,6 +137,7 @@ k_gemm_tc(Prod prod, const uint32_t* __restrict__ Bimg, const float* __restrict_
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     const int n0 = blockIdx.y * NT;                          // first column of this CTA's N tile
+    for (int j = tid; j < NT; j += TC_THREADS) bias_s[j] = (bias && n0 + j < N) ? __ldg(bias + n0 + j) : 0.f;
     const int tiles_m = (M + TC_BM - 1) / TC_BM;
     const int my_tiles = blockIdx.x < tiles_m ? (tiles_m - 1 - blockIdx.x) / gridDim.x + 1 : 0;
 
@@ -168,6 +170,17 @@ k_gemm_tc(Prod prod, const uint32_t* __restrict__ Bimg, const float* __restrict_
     };
     const uint32_t total = (uint32_t)my_tiles * (uint32_t)kchunks;
     if (total) prefetch(0, 0);
+    // B chunk of iteration `it` → stage it&1, issued ONE iteration ahead (right after the MMAs of it-1 are
+    // queued) so that the bulk copy's latency hides behind those MMAs and the next A staging
+    auto issue_b = [&](uint32_t it, int kc_b) {
+        const int sb = it & 1;
+        uint8_t* b_dst = smem + (size_t)sb * STAGE + 2 * TcSmem::A_TILE;
+        mbar_expect_tx(&tma_bar[sb], 2 * B_TILE);
+        const uint32_t* src = Bimg + (size_t)kc_b * 2 * n_pad_total * TC_BK;
+        bulk_g2s(b_dst, src + (size_t)n0 * TC_BK, B_TILE, &tma_bar[sb]);
+        bulk_g2s(b_dst + B_TILE, src + ((size_t)n_pad_total + n0) * TC_BK, B_TILE, &tma_bar[sb]);
+    };
+    if (total && tid == 0) issue_b(0, 0);
 
     int tile_idx = 0, kc = 0;
     for (uint32_t it = 0; it < total; ++it) {
@@ -178,12 +191,6 @@ k_gemm_tc(Prod prod, const uint32_t* __restrict__ Bimg, const float* __restrict_
         uint8_t* a_lo = st + TcSmem::A_TILE;
         uint8_t* b_hi = st + 2 * TcSmem::A_TILE;            // [hi | lo] contiguous, as in the packed image
         if (use > 0) mbar_wait(&mma_bar[s], (use - 1) & 1);  // MMAs that read this stage have completed
-        if (tid == 0) {
-            mbar_expect_tx(&tma_bar[s], 2 * B_TILE);
-            const uint32_t* src = Bimg + (size_t)kc * 2 * n_pad_total * TC_BK;
-            bulk_g2s(b_hi, src + (size_t)n0 * TC_BK, B_TILE, &tma_bar[s]);
-            bulk_g2s(b_hi + B_TILE, src + ((size_t)n_pad_total + n0) * TC_BK, B_TILE, &tma_bar[s]);
-        }
         {
             const int b = tile_idx & 1;
 #pragma unroll
@@ -215,6 +222,11 @@ k_gemm_tc(Prod prod, const uint32_t* __restrict__ Bimg, const float* __restrict_
         }
         // next chunk's global loads fly while the MMAs run (and, at a tile end, during the epilogue)
         const bool tile_end = kc + 1 == kchunks;
+        if (tid == 0 && it + 1 < total) {
+            const uint32_t use1 = (it + 1) >> 1;             // the other stage: free once the MMAs of it-1 are done
+            if (use1 > 0) mbar_wait(&mma_bar[s ^ 1], (use1 - 1) & 1);
+            issue_b(it + 1, tile_end ? 0 : kc + 1);
+        }
         if (it + 1 < total) prefetch(tile_end ? tile_idx + 1 : tile_idx, tile_end ? 0 : kc + 1);
         if (tile_end) {
             // ---- epilogue: the last commit covers every MMA of the tile
@@ -239,12 +251,14 @@ k_gemm_tc(Prod prod, const uint32_t* __restrict__ Bimg, const float* __restrict_
                         for (int j = 0; j < 32; j += 4) {
                             const int col = n0 + c0 + j;
                             if (j >= lim || col >= N) continue;
-                            float x[4];
+                            // bias from shared memory (one broadcast float4 per four columns): a global load per
+                            // element here was the kernel's top stall (ncu r1c: FADD waiting on long_scoreboard)
+                            const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c0 + j);
+                            float x[4] = {__uint_as_float(v[j]) + b4.x, __uint_as_float(v[j + 1]) + b4.y,
+                                          __uint_as_float(v[j + 2]) + b4.z, __uint_as_float(v[j + 3]) + b4.w};
+                            if (relu) {
 #pragma unroll
-                            for (int u = 0; u < 4; ++u) {
-                                x[u] = __uint_as_float(v[j + u]);
-                                if (bias && col + u < N) x[u] += __ldg(bias + col + u);
-                                if (relu) x[u] = fmaxf(x[u], 0.f);
+                                for (int u = 0; u < 4; ++u) x[u] = fmaxf(x[u], 0.f);
                             }
                             if (vec4 && j + 4 <= lim && col + 4 <= N) {
                                 *reinterpret_cast<float4*>(dst + col) = make_float4(x[0], x[1], x[2], x[3]);
