@@ -126,7 +126,9 @@ k_spmm_vec(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indic
     }
 }
 
-// rows split over several segments: sum the partial rows in segment order, then bias / ReLU
+// rows split over several segments: sum the partial rows in segment order, then bias / ReLU.
+// One warp per row; a lane owns one float4 column slice (d ≤ 128: one pass) and keeps 8 loads in flight —
+// a hub row has hundreds of segments, and one dependent load per segment made this the tail of the SpMM.
 __global__ void k_spmm_fixup(const int32_t* __restrict__ seg_off, const int32_t* __restrict__ sel, int32_t n_rows,
                              const float* __restrict__ partial, int32_t d, const float* __restrict__ bias, int relu,
                              float* __restrict__ C, int64_t ldc) {
@@ -136,12 +138,28 @@ __global__ void k_spmm_fixup(const int32_t* __restrict__ seg_off, const int32_t*
     const int32_t first = seg_off[i], nseg = seg_off[i + 1] - first;
     if (nseg <= 1) return;
     const int64_t il = list_pos(sel, i);
-    for (int col = lane; col < d; col += 32) {
-        float a = 0.f;
-        for (int32_t sgm = 0; sgm < nseg; ++sgm) a += partial[(int64_t)(first + sgm) * d + col];
-        if (bias) a += bias[col];
-        if (relu) a = fmaxf(a, 0.f);
-        C[il * ldc + col] = a;
+    const int d4 = d >> 2;                                   // the vector path guarantees d % 4 == 0
+    const float4* P4 = reinterpret_cast<const float4*>(partial) + (int64_t)first * d4;
+    for (int col = lane; col < d4; col += 32) {
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        int32_t sgm = 0;
+        for (; sgm + 8 <= nseg; sgm += 8) {
+            float4 p[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) p[u] = P4[(int64_t)(sgm + u) * d4 + col];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { a.x += p[u].x; a.y += p[u].y; a.z += p[u].z; a.w += p[u].w; }
+        }
+        for (; sgm < nseg; ++sgm) {
+            const float4 p = P4[(int64_t)sgm * d4 + col];
+            a.x += p.x; a.y += p.y; a.z += p.z; a.w += p.w;
+        }
+        if (bias) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(bias) + col);
+            a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+        }
+        if (relu) { a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f); }
+        reinterpret_cast<float4*>(C + il * ldc)[col] = a;
     }
 }
 
