@@ -174,6 +174,19 @@ int lt_rank_curve(const float* scores, const uint8_t* labels, int64_t n_pairs, f
 int lt_lsa2_corr(const float* M, int64_t ldm, int32_t d, const int32_t* test_nodes, int32_t T,
                  int transform, float* dist, int64_t ldd, lt_stream_t stream);
 
+/* f2  baseline_attack_balanced (attacker.py:337-375, --sample-type balanced-full): the same centred
+ *     cosine similarity for LISTED pairs (pu[k], pv[k]); the mean runs over ALL n_rows rows of M
+ *     (attacker.py:361), out[k] in list order. */
+int lt_lsa2_pairs(const float* M, int64_t ldm, int32_t n_rows, int32_t d, int transform, const int32_t* pu,
+                  const int32_t* pv, int64_t n_pairs, float* out, lt_stream_t stream);
+
+/* f2/f4  link_prediction_attack_efficient_balanced (attacker.py:250-284) and the naive per-pair attack
+ *     (attacker.py:143-160 → get_gradient_eps :87-97) read single entries grad_mat(perturbed)[observed]:
+ *     out[k] = block[(rows[k] − row0)·ld + cols[k]] for the pairs whose perturbed node lies in the
+ *     block of influence rows [row0, row0 + n_rows) that lt_attack_efficient just produced. */
+int lt_pair_gather(const float* block, int64_t ld, int32_t row0, int32_t n_rows, const int32_t* rows,
+                   const int32_t* cols, int64_t n_pairs, float* out, lt_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * a11 perturb_adj_discrete (EdgeRand), worker.py:213-278: the Bernoulli hits and their add/remove
  *     coin are drawn on the HOST from numpy's legacy stream (same seed ⇒ same flips); the device

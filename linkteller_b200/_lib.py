@@ -48,6 +48,8 @@ _SIGS = {
     "lt_topk_tp": [P, P, I64, P, I32, P, P, P],
     "lt_rank_curve": [P, P, I64, P, P, P, I64, P, P],
     "lt_lsa2_corr": [P, I64, I32, P, I32, INT, P, I64, P],
+    "lt_lsa2_pairs": [P, I64, I32, I32, INT, P, P, I64, P, P],
+    "lt_pair_gather": [P, I64, I32, I32, P, P, I64, P, P],
     "lt_dp_edgerand_apply": [P, P, P, I32, P, P, I64, P, P, P, I64, P, P],
     "lt_dp_lapgraph_select": [P, P, P, I32, P, I64, P, P, P, I64, P, P],
     "lt_launch_count": [],

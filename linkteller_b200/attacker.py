@@ -135,12 +135,13 @@ class Attacker:
         st = self.args.sample_type
         if st not in SAMPLE_TYPES:
             raise NotImplementedError(f'sample_type = {st} not implemented!')
-        if st in ('balanced', 'bfs', 'balanced-full'):
-            # 'balanced' and 'bfs' crash upstream (ValueError / TypeError); 'balanced-full'
-            # is the next row of the scope table (§8 f2)
+        if st in ('balanced', 'bfs'):
+            # both crash upstream (ValueError / TypeError)
             raise NotImplementedError(f'sample_type = {st} is outside the accelerated path '
-                                      '(unbalanced, unbalanced-lo, unbalanced-hi)')
+                                      '(unbalanced, unbalanced-lo, unbalanced-hi, balanced-full)')
         ori = self._adj_ori_device()
+        if st == 'balanced-full':
+            return self._prepare_balanced_full(ori)
         indptr = ori.indptr.cpu().numpy()
         # np.random.seed(sample_seed) + np.random.choice(candidates, T, replace=False)  (attacker.py:45, load.py:379)
         self.test_nodes = workloads.sample_test_nodes_typed(self.dataset, st, indptr, self.args.n_test,
@@ -158,6 +159,41 @@ class Attacker:
         print('#nodes =', T)
         print('#edges_set =', len(self.exist_edges))
         print('#nonedge_set =', len(self.nonexist_edges))
+        print(f'generating testing (non-)edge set done!')
+
+    def _prepare_balanced_full(self, ori):
+        """construct_balanced_edge_sets (utils/load.py:219-249): every edge u<v of adj_ori in row order
+        and as many non-edges drawn by rejection from numpy's legacy stream.  The stream is consumed
+        exactly as upstream does (np.random.choice(n) per endpoint ≡ one randint(0, n) draw), in
+        batches; the O(n·deg) Python membership tests become sorted-key lookups."""
+        n = ori.n
+        indptr = ori.indptr.cpu().numpy().astype(np.int64)
+        indices = ori.indices.cpu().numpy().astype(np.int64)
+        row = np.repeat(np.arange(n, dtype=np.int64), np.diff(indptr))
+        up = indices > row
+        edges = np.stack([row[up], indices[up]], axis=1)
+        keys = row * n + indices                      # ascending: CSR rows are sorted
+        rs = np.random.RandomState(self.args.sample_seed)            # attacker.py:45
+        need, got = len(edges), []
+        if need == 0:
+            raise ValueError("balanced-full needs at least one edge (upstream loops forever here)")
+        while need > 0:
+            draw = rs.randint(0, n, size=2 * max(1024, int(need * 1.2)))
+            u, v = draw[0::2].astype(np.int64), draw[1::2].astype(np.int64)
+            def stored(a, b):
+                k = a * n + b
+                p = np.searchsorted(keys, k)
+                return (p < len(keys)) & (keys[np.minimum(p, len(keys) - 1)] == k)
+            ok = ~stored(u, v) & ~stored(v, u)        # load.py:244
+            take = np.flatnonzero(ok)[:need]
+            got.append(np.stack([u[take], v[take]], axis=1))
+            need -= len(take)
+        nonedges = np.concatenate(got)
+        print(f'sampling done! len(edge_set) = {len(edges)}, len(nonedge_set) = {len(nonedges)}')
+        self.test_nodes = list(range(n))
+        self.exist_edges = PairList(edges)
+        self.nonexist_edges = PairList(nonedges)
+        self._labels = None
         print(f'generating testing (non-)edge set done!')
 
     def _n_candidates(self, indptr, st):
@@ -195,6 +231,79 @@ class Attacker:
         self.influence_val = infl
         self._finish(scores)
 
+    # ------------------------------------------------------------------ f2 / f4
+    def _pair_tensors(self, prs):
+        a = np.asarray(prs).reshape(-1, 2)
+        return (torch.from_numpy(a[:, 0].astype(np.int32)).to(self.device),
+                torch.from_numpy(a[:, 1].astype(np.int32)).to(self.device))
+
+    def _listed_influence(self, prs, perturb_first: bool) -> np.ndarray:
+        d = self._staged()
+        u, v = self._pair_tensors(prs)
+        p, o = (u, v) if perturb_first else (v, u)
+        sc = ops.pair_influence(d["hat"], d["x"], d["w1"], d["b1"], d["w2"], p, o, float(self.args.influence))
+        return sc.cpu().numpy().astype(np.float64)
+
+    def link_prediction_attack_efficient_balanced(self):
+        """attacker.py:250-284 (--sample-type balanced-full): score(u,v) = ‖get_gradient_eps_mat(u)[v]‖ —
+        perturb the FIRST node of the pair; each list comes out ordered by u, then by list position."""
+        t = time.time()
+        outs = []
+        for prs in (self.exist_edges, self.nonexist_edges):
+            sc = self._listed_influence(prs, perturb_first=True)
+            order = np.argsort(np.asarray(prs).reshape(-1, 2)[:, 0], kind="stable")
+            outs.append(sc[order])
+        torch.cuda.synchronize(self.device)
+        print(f'time for predicting edges: {time.time() - t}')
+        self.compute_and_save(outs[0], outs[1])
+
+    def link_prediction_attack(self):
+        """The naive per-pair attack (attacker.py:143-206): score(u,v) = ‖get_gradient_eps(u, v)‖ =
+        ‖grad_mat(v)[u]‖ (:87-97).  Same numbers as the efficient attack, one entry at a time upstream;
+        here the listed entries are gathered from blocks of influence rows.  Keeps upstream's file
+        name (no attack_mode prefix, :180-183)."""
+        t = time.time()
+        if self.args.sample_type == 'balanced-full':
+            listed = lambda prs: self._listed_influence(prs, perturb_first=False)
+        else:
+            # pairs among the T sampled nodes: their entries all live in the T x T influence matrix
+            infl = self.influence_matrix()
+            pos = {int(nd): i for i, nd in enumerate(np.asarray(self.test_nodes))}
+
+            def listed(prs):
+                a = np.asarray(prs).reshape(-1, 2)
+                rows = torch.tensor([pos[int(v)] for v in a[:, 1]], dtype=torch.int32, device=self.device)
+                cols = torch.tensor([pos[int(u)] for u in a[:, 0]], dtype=torch.int32, device=self.device)
+                return ops.pair_gather(infl, rows, cols).cpu().numpy().astype(np.float64)
+        ex = listed(self.exist_edges)
+        torch.cuda.synchronize(self.device)
+        print(f'time for predicting existing edges: {time.time() - t}')
+        t = time.time()
+        ne = listed(self.nonexist_edges)
+        torch.cuda.synchronize(self.device)
+        print(f'time for predicting non-existing edges: {time.time() - t}')
+        return self.compute_and_save(ex, ne, naive_name=True)
+
+    def baseline_attack_balanced(self):
+        """attacker.py:337-375: LSA2 on listed pairs, mean over ALL nodes (:361), list order kept."""
+        t = time.time()
+        d = self._staged()
+        mode = self.args.attack_mode
+        if mode == 'baseline':
+            mat = ops.gcn_forward(d["hat"], d["x"], d["w1"], d["b1"], d["w2"], d["b2"])
+            tr = "sigmoid" if self.dataset == 'ppi' else "softmax"
+        elif mode == 'baseline-feat':
+            mat, tr = d["x"], "none"
+        else:
+            raise NotImplementedError(f'attack_mode={mode} not implemented!')
+        outs = []
+        for prs in (self.exist_edges, self.nonexist_edges):
+            u, v = self._pair_tensors(prs)
+            outs.append(ops.lsa2_pairs(mat, u, v, tr).cpu().numpy().astype(np.float64))
+        torch.cuda.synchronize(self.device)
+        print(f'time for computing correlation value: {time.time() - t}')
+        self.compute_and_save(outs[0], outs[1])
+
     # ------------------------------------------------------------------ a10
     def baseline_attack(self):
         t = time.time()
@@ -224,7 +333,7 @@ class Attacker:
         lab = labels.cpu().numpy().astype(bool)
         self.compute_and_save(sc[lab].astype(np.float64), sc[~lab].astype(np.float64))
 
-    def compute_and_save(self, norm_exist, norm_nonexist):
+    def compute_and_save(self, norm_exist, norm_nonexist, naive_name: bool = False):
         norm_exist = np.asarray(norm_exist, dtype=np.float64)
         norm_nonexist = np.asarray(norm_nonexist, dtype=np.float64)
         y = np.r_[np.ones(len(norm_exist), dtype=np.int64), np.zeros(len(norm_nonexist), dtype=np.int64)]
@@ -242,10 +351,11 @@ class Attacker:
         folder_name = f'eval_{self.dataset}'
         if not osp.exists(folder_name):
             os.makedirs(folder_name)
+        prefix = '' if naive_name else f'{self.args.attack_mode}_'          # attacker.py:180-183 vs :391-394
         if self.args.mode == 'vanilla-clean':
-            filename = osp.join(folder_name, f'{self.args.attack_mode}_{self.args.sample_type}_{self.args.n_test}_{self.args.sample_seed}.pt')
+            filename = osp.join(folder_name, f'{prefix}{self.args.sample_type}_{self.args.n_test}_{self.args.sample_seed}.pt')
         else:
-            filename = osp.join(folder_name, f'{self.args.attack_mode}_{self.args.sample_type}_{self.args.perturb_type}_{self.args.n_test}_{self.args.sample_seed}_eps-{self.args.epsilon}_seed-{self.args.noise_seed}.pt')
+            filename = osp.join(folder_name, f'{prefix}{self.args.sample_type}_{self.args.perturb_type}_{self.args.n_test}_{self.args.sample_seed}_eps-{self.args.epsilon}_seed-{self.args.noise_seed}.pt')
         big = len(pred) > 5_000_000      # the reference stores Python lists; keep arrays past 5 M pairs
         torch.save({
             'auc': {'fpr': fpr, 'tpr': tpr, 'thresholds': thresholds},

@@ -18,7 +18,7 @@ k_lsa2_rows(const float* __restrict__ M, int64_t ldm, int32_t d, const int32_t* 
     const int lane = threadIdx.x & 31;
     const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (i >= T) return;
-    const float* src = M + (int64_t)test_nodes[i] * ldm;
+    const float* src = M + (int64_t)(test_nodes ? test_nodes[i] : (int32_t)i) * ldm;   // null list: all rows in order
     float* dst = sub + i * d;
     if (transform == 1) {            // softmax(dim=1): exp(x − max) / Σ
         float mx = -INFINITY;
@@ -62,6 +62,40 @@ k_lsa2_centre(float* __restrict__ sub, int32_t T, int32_t d, const float* __rest
     if (lane == 0) nrm[i] = sqrtf(ss);
 }
 
+// mean over many rows in two deterministic levels: part[b,:] = Σ of rows b·chunk … (one thread per column)
+__global__ void k_lsa2_partial(const float* __restrict__ sub, int32_t T, int32_t d, int32_t chunk, float* __restrict__ part) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
+    if (k >= d) return;
+    const int i0 = b * chunk, i1 = min(T, i0 + chunk);
+    float s = 0.f;
+    for (int i = i0; i < i1; ++i) s += sub[(int64_t)i * d + k];
+    part[(int64_t)b * d + k] = s;
+}
+__global__ void k_lsa2_mean_of_parts(const float* __restrict__ part, int32_t nb, int32_t d, int32_t T, float* __restrict__ mean) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= d) return;
+    float s = 0.f;
+    for (int b = 0; b < nb; ++b) s += part[(int64_t)b * d + k];
+    mean[k] = s / (float)T;
+}
+
+// one warp per listed pair: <c_u, c_v> / ‖c_u‖ / ‖c_v‖ on the centred rows (attacker.py:364-368)
+__global__ void __launch_bounds__(256)
+k_lsa2_pairs(const float* __restrict__ cen, int32_t d, const float* __restrict__ nrm, const int32_t* __restrict__ pu,
+             const int32_t* __restrict__ pv, int64_t K, float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t k = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (k >= K) return;
+    const int32_t u = pu[k], v = pv[k];
+    const float* a = cen + (int64_t)u * d;
+    const float* b = cen + (int64_t)v * d;
+    float s = 0.f;
+    for (int c = lane; c < d; c += 32) s = fmaf(a[c], b[c], s);
+    s = warp_sum(s);
+    if (lane == 0) out[k] = (s / nrm[u]) / nrm[v];
+}
+
 // dist[i][j] = gram/‖i‖/‖j‖ for i<j, 0 elsewhere (attacker.py:316: dot / norm / norm, in that order)
 __global__ void k_lsa2_scale(float* __restrict__ dist, int64_t ldd, int32_t T, const float* __restrict__ nrm) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -95,6 +129,33 @@ extern "C" int lt_lsa2_corr(const float* M, int64_t ldm, int32_t d, const int32_
     LT_LAUNCH_CHECK();
     LT_TRY(gemm_f32(sub, d, nullptr, sub, d, 1, nullptr, 0, dist, ldd, T, T, d, 1, s));
     k_lsa2_scale<<<dim3((unsigned)ceil_div(T, 256), (unsigned)T), 256, 0, s>>>(dist, ldd, T, nrm);
+    LT_LAUNCH_CHECK();
+    return LT_OK;
+}
+
+extern "C" int lt_lsa2_pairs(const float* M, int64_t ldm, int32_t n_rows, int32_t d, int transform, const int32_t* pu,
+                             const int32_t* pv, int64_t n_pairs, float* out, lt_stream_t stream) {
+    LT_CHECK_ARG(M && pu && pv && out && d > 0 && n_rows > 0 && ldm >= d && n_pairs >= 0, "lt_lsa2_pairs");
+    LT_CHECK_ARG(transform >= 0 && transform <= 2, "lt_lsa2_pairs: transform");
+    if (n_pairs == 0) return LT_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    Scratch scratch(s);
+    const int32_t chunk = 1024, nb = (int32_t)ceil_div(n_rows, chunk);
+    float *sub, *part, *mean, *nrm;
+    LT_TRY(scratch.alloc(&sub, (size_t)n_rows * d));
+    LT_TRY(scratch.alloc(&part, (size_t)nb * d));
+    LT_TRY(scratch.alloc(&mean, (size_t)d));
+    LT_TRY(scratch.alloc(&nrm, (size_t)n_rows));
+    const unsigned blT = (unsigned)ceil_div((int64_t)n_rows * 32, 256);
+    k_lsa2_rows<<<blT, 256, 0, s>>>(M, ldm, d, nullptr, n_rows, transform, sub);
+    LT_LAUNCH_CHECK();
+    k_lsa2_partial<<<dim3((unsigned)ceil_div(d, 128), (unsigned)nb), 128, 0, s>>>(sub, n_rows, d, chunk, part);
+    LT_LAUNCH_CHECK();
+    k_lsa2_mean_of_parts<<<(unsigned)ceil_div(d, 128), 128, 0, s>>>(part, nb, d, n_rows, mean);
+    LT_LAUNCH_CHECK();
+    k_lsa2_centre<<<blT, 256, 0, s>>>(sub, n_rows, d, mean, nrm);
+    LT_LAUNCH_CHECK();
+    k_lsa2_pairs<<<(unsigned)ceil_div(n_pairs * 32, 256), 256, 0, s>>>(sub, d, nrm, pu, pv, n_pairs, out);
     LT_LAUNCH_CHECK();
     return LT_OK;
 }

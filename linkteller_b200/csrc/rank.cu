@@ -67,6 +67,16 @@ k_pair_scores(const float* __restrict__ infl, int64_t ldi, int32_t T, float* __r
     }
 }
 
+// listed pairs: out[k] = block[(rows[k] − row0)·ld + cols[k]] for the pairs whose row lies in [row0, row0+n_rows)
+__global__ void k_pair_gather(const float* __restrict__ block, int64_t ld, int32_t row0, int32_t n_rows,
+                              const int32_t* __restrict__ rows, const int32_t* __restrict__ cols, int64_t K,
+                              float* __restrict__ out) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= K) return;
+    const int32_t r = rows[k] - row0;
+    if (r >= 0 && r < n_rows) out[k] = block[(int64_t)r * ld + cols[k]];
+}
+
 // ------------------------------------------------------------------------------------ ranking
 // descending order of float scores = ascending order of ~sortable(bits)
 __device__ __forceinline__ uint32_t desc_key(float f) {
@@ -268,6 +278,16 @@ extern "C" int lt_pair_scores(const float* influence, int64_t ldi, int32_t T, fl
     const unsigned nb = (unsigned)ceil_div(T, 32);
     LT_CHECK_ARG(nb <= 65535, "lt_pair_scores: T too large");
     k_pair_scores<<<dim3(nb, nb), 256, 0, (cudaStream_t)stream>>>(influence, ldi, T, scores);
+    LT_LAUNCH_CHECK();
+    return LT_OK;
+}
+
+extern "C" int lt_pair_gather(const float* block, int64_t ld, int32_t row0, int32_t n_rows, const int32_t* rows,
+                              const int32_t* cols, int64_t n_pairs, float* out, lt_stream_t stream) {
+    LT_CHECK_ARG(block && rows && cols && out && ld > 0 && n_rows >= 0 && n_pairs >= 0, "lt_pair_gather");
+    if (n_pairs == 0 || n_rows == 0) return LT_OK;
+    k_pair_gather<<<(unsigned)ceil_div(n_pairs, 256), 256, 0, (cudaStream_t)stream>>>(block, ld, row0, n_rows, rows, cols,
+                                                                                  n_pairs, out);
     LT_LAUNCH_CHECK();
     return LT_OK;
 }

@@ -420,6 +420,78 @@ def lsa2_corr(mat: torch.Tensor, test_nodes: torch.Tensor, transform: str = "non
     return dist
 
 
+def lsa2_pairs(mat: torch.Tensor, pu: torch.Tensor, pv: torch.Tensor, transform: str = "none") -> torch.Tensor:
+    """baseline_attack_balanced (attacker.py:337-375): centred cosine similarity of LISTED pairs, the
+    mean taken over all rows of `mat`; float32 [K] in list order."""
+    lib = _lib.load()
+    mat, ldm = _rowmajor(mat, "mat")
+    _chk(pu, torch.int32, "pu", 1)
+    _chk(pv, torch.int32, "pv", 1)
+    K = pu.numel()
+    if pv.numel() != K:
+        raise ValueError("pu and pv must have the same length")
+    n = mat.shape[0]
+    if K and (int(torch.minimum(pu.min(), pv.min())) < 0 or int(torch.maximum(pu.max(), pv.max())) >= n):
+        raise IndexError("pair node outside the matrix")
+    out = torch.empty(max(K, 1), dtype=torch.float32, device=mat.device)
+    _lib.check(lib.lt_lsa2_pairs(_p(mat), ldm, n, mat.shape[1], LSA2_TRANSFORMS[transform], _p(pu), _p(pv), K, _p(out),
+                                 _stream()), "lt_lsa2_pairs")
+    return out[:K]
+
+
+def pair_gather(mat: torch.Tensor, rows: torch.Tensor, cols: torch.Tensor, row0: int = 0) -> torch.Tensor:
+    """out[k] = mat[rows[k] − row0, cols[k]] for the listed entries whose row lies inside `mat`
+    (others 0) — lt_pair_gather."""
+    lib = _lib.load()
+    mat, ld = _rowmajor(mat, "mat")
+    _chk(rows, torch.int32, "rows", 1)
+    _chk(cols, torch.int32, "cols", 1)
+    K = rows.numel()
+    if cols.numel() != K:
+        raise ValueError("rows and cols must have the same length")
+    if K and (int(cols.min()) < 0 or int(cols.max()) >= mat.shape[1]):
+        raise IndexError("column outside the matrix")
+    out = torch.zeros(max(K, 1), dtype=torch.float32, device=mat.device)
+    _lib.check(lib.lt_pair_gather(_p(mat), ld, row0, mat.shape[0], _p(rows), _p(cols), K, _p(out), _stream()),
+               "lt_pair_gather")
+    return out[:K]
+
+
+def pair_influence(adj: DeviceCSR, x, w1, b1, w2, perturbed: torch.Tensor, observed: torch.Tensor, delta: float,
+                   block_bytes: int = 512 << 20) -> torch.Tensor:
+    """‖((f(X + δ·e_p x_pᵀ) − f(X))/δ)[o]‖₂ for LISTED (perturbed p, observed o) node pairs — what
+    link_prediction_attack_efficient_balanced (attacker.py:250-284) and the naive attack
+    (attacker.py:143-160) read one entry at a time.  Every node is a candidate observer, so influence
+    rows are produced in blocks of perturbed nodes (lt_attack_efficient over [lo,hi) of 0..n-1, at most
+    block_bytes of rows at a time) and the listed entries are gathered from each block.  float32 [K]."""
+    lib = _lib.load()
+    _chk(perturbed, torch.int32, "perturbed", 1)
+    _chk(observed, torch.int32, "observed", 1)
+    K = perturbed.numel()
+    if observed.numel() != K:
+        raise ValueError("perturbed and observed must have the same length")
+    n = adj.n
+    out = torch.zeros(max(K, 1), dtype=torch.float32, device=x.device)
+    if K == 0:
+        return out[:0]
+    if int(torch.minimum(perturbed.min(), observed.min())) < 0 or int(torch.maximum(perturbed.max(), observed.max())) >= n:
+        raise IndexError("pair node outside the graph")
+    all_nodes = torch.arange(n, dtype=torch.int32, device=x.device)
+    need = torch.zeros(n, dtype=torch.bool, device=x.device)
+    need[perturbed.long()] = True
+    need = need.cpu().numpy()
+    rows_per_block = max(1, min(n, block_bytes // (4 * n)))
+    buf = torch.empty((rows_per_block, n), dtype=torch.float32, device=x.device)
+    for lo in range(0, n, rows_per_block):
+        hi = min(n, lo + rows_per_block)
+        if not need[lo:hi].any():
+            continue
+        attack_efficient(adj, x, w1, b1, w2, all_nodes, delta, lo=lo, hi=hi, out=buf[: hi - lo])
+        _lib.check(lib.lt_pair_gather(_p(buf), buf.stride(0), lo, hi - lo, _p(perturbed), _p(observed), K, _p(out),
+                                      _stream()), "lt_pair_gather")
+    return out[:K]
+
+
 # ------------------------------------------------------------------------------------------ a11/a12
 def dp_edgerand_apply(adj: DeviceCSR, hits: torch.Tensor, coin: torch.Tensor) -> DeviceCSR:
     """adj + add − minus with −1→0, 2→1 (worker.py:264-267) from host-drawn flips.  hits: int64 cell

@@ -347,6 +347,101 @@ def posterior(logits, dataset):
 
 
 # --------------------------------------------------------------------------------------------
+# f2 / f4  the "next" rows of SURVEY.md §8f: --sample-type balanced-full
+#          (construct_balanced_edge_sets, utils/load.py:219-249;
+#          link_prediction_attack_efficient_balanced, attacker.py:250-284;
+#          baseline_attack_balanced, attacker.py:337-375) and the naive per-pair attack
+#          (link_prediction_attack, attacker.py:143-160 → get_gradient_eps, :87-97)
+# --------------------------------------------------------------------------------------------
+
+def balanced_edge_sets(indptr, indices, sample_seed):
+    """Every edge u<v of adj_ori in row order (load.py:233-237) and as many non-edges drawn by
+    rejection from numpy's legacy stream, one np.random.choice(n) per endpoint (load.py:241-246;
+    the stream is seeded by attacker.py:45).  Returns (edge [m,2], nonedge [m,2], test_nodes)."""
+    indptr, indices = np.asarray(indptr), np.asarray(indices)
+    n = len(indptr) - 1
+    rows = [indices[indptr[u]:indptr[u + 1]] for u in range(n)]
+    edge = [(u, int(v)) for u in range(n) for v in rows[u] if v > u]
+    rs = np.random.RandomState(sample_seed)
+    non = []
+    while len(non) < len(edge):
+        u = rs.choice(n)
+        v = rs.choice(n)
+        if v not in rows[u] and u not in rows[v]:
+            non.append((int(u), int(v)))
+    return (np.asarray(edge, dtype=np.int64).reshape(-1, 2), np.asarray(non, dtype=np.int64).reshape(-1, 2),
+            np.arange(n))
+
+
+def _grad_mat(x, adj, w, v, delta):
+    pert = torch.zeros_like(x)
+    pert[v] = x[v] * delta
+    return (gcn_forward(x + pert, adj, *w) - gcn_forward(x, adj, *w)) / delta
+
+
+def _tensors(X, coo, weights, n, dtype):
+    row, col, val = coo
+    adj = _sparse(row, col, val, n, dtype)
+    x = torch.from_numpy(np.asarray(X)).to(dtype)
+    w = [torch.from_numpy(np.asarray(a)).to(dtype) for a in weights]
+    return x, adj, w
+
+
+def efficient_balanced_scores(X, coo, weights, n, exist, nonexist, delta, dtype=torch.float64):
+    """attacker.py:250-284: for u = 0..n-1 with listed pairs, grad_mat = get_gradient_eps_mat(u) and
+    the score of (u,v) is ‖grad_mat[v]‖ — PERTURB THE FIRST node, observe the second.  The two
+    output lists are ordered by u, then by position in the input list (the dict-of-lists order)."""
+    x, adj, w = _tensors(X, coo, weights, n, dtype)
+    outs = []
+    with torch.no_grad():
+        for prs in (np.asarray(exist).reshape(-1, 2), np.asarray(nonexist).reshape(-1, 2)):
+            order = np.argsort(prs[:, 0], kind="stable")
+            res = np.zeros(len(prs))
+            cur, g = -1, None
+            for k in order:
+                u, v = int(prs[k, 0]), int(prs[k, 1])
+                if u != cur:
+                    cur, g = u, _grad_mat(x, adj, w, u, delta)
+                res[k] = g[v].norm().item()
+            outs.append(res[order])
+    return outs[0], outs[1]
+
+
+def naive_scores(X, coo, weights, n, exist, nonexist, delta, dtype=torch.float64):
+    """attacker.py:143-160: score(u,v) = ‖get_gradient_eps(u, v)‖ = ‖grad_mat(v)[u]‖ — perturb the
+    SECOND node, observe the first (attacker.py:87-97); list order kept."""
+    x, adj, w = _tensors(X, coo, weights, n, dtype)
+    outs = []
+    with torch.no_grad():
+        for prs in (np.asarray(exist).reshape(-1, 2), np.asarray(nonexist).reshape(-1, 2)):
+            res = np.zeros(len(prs))
+            cache = {}
+            for k, (u, v) in enumerate(prs):
+                v = int(v)
+                if v not in cache:
+                    if len(cache) > 8:
+                        cache.clear()
+                    cache[v] = _grad_mat(x, adj, w, v, delta)
+                res[k] = cache[v][int(u)].norm().item()
+            outs.append(res)
+    return outs[0], outs[1]
+
+
+def lsa2_balanced(posterior_or_feats, exist, nonexist):
+    """attacker.py:337-375: mean over ALL rows (:361), then per listed pair
+    <p_u−m, p_v−m> / ‖p_u−m‖ / ‖p_v−m‖ in list order (:364-368); float32 arithmetic."""
+    p = torch.as_tensor(np.asarray(posterior_or_feats))
+    cen = p - torch.mean(p, dim=0)
+    nrm = torch.norm(cen, dim=1)
+    outs = []
+    for prs in (np.asarray(exist).reshape(-1, 2), np.asarray(nonexist).reshape(-1, 2)):
+        u = torch.from_numpy(prs[:, 0].astype(np.int64))
+        v = torch.from_numpy(prs[:, 1].astype(np.int64))
+        outs.append(((cen[u] * cen[v]).sum(dim=1) / nrm[u] / nrm[v]).double().numpy())
+    return outs[0], outs[1]
+
+
+# --------------------------------------------------------------------------------------------
 # a11  perturb_adj_discrete — EdgeRand (worker.py:213-278) + construct_sparse_mat (:178-203)
 # --------------------------------------------------------------------------------------------
 

@@ -171,8 +171,82 @@ def run_case(name, shape, seed, hidden, norm, sample_type, dataset, T, dp=None, 
           f"auc={out['a9_auc']:.4f} → {os.path.getsize(path) / 1024:.0f} KiB")
 
 
+def run_case_next(name, shape, seed, hidden, T_naive=12):
+    """--sample-type balanced-full (construct_balanced_edge_sets,
+    link_prediction_attack_efficient_balanced, baseline_attack_balanced) and the naive per-pair attack
+    (link_prediction_attack) — the reference's own outputs, float32 as shipped and float64."""
+    s = synth.make(shape, seed=seed, hidden=hidden)
+    n, f, c = s.n, s.f, s.c
+    weights = synth.gcn_weights(f, hidden, c, seed=42)
+    out = dict(shape=shape, seed=seed, hidden=hidden, norm="FirstOrderGCN", delta=1e-4, sample_seed=42,
+               T_naive=T_naive)
+    adj_ori = ref_graph_reader(s.edges, n, "twitch/ES/RU").tocsr()
+    adj_ori.sort_indices()
+    coo = ref_utils.fetch_normalization("FirstOrderGCN")(adj_ori)
+    adj_t = quiet(ref_utils.sparse_mx_to_torch_sparse_tensor, coo)
+    X = torch.from_numpy(s.features)
+    base = dict(dataset="twitch/ES/RU", influence=1e-4, sample_seed=42, mode="vanilla-clean", perturb_type=None,
+                epsilon=5.0, noise_seed=42)
+    for tag, dbl in (("32", False), ("64", True)):
+        model = build_model(f, hidden, c, weights, double=dbl)
+        feats = X.double() if dbl else X
+        adj = adj_t.double() if dbl else adj_t
+        wk = types.SimpleNamespace(n_nodes=n, n_features=f, features=feats, adj_full=adj, features_2=feats,
+                                   adj_2=adj, adj_ori=adj_ori)
+        # ---- balanced-full, efficient
+        args = types.SimpleNamespace(sample_type="balanced-full", n_test=0, attack_mode="efficient", **base)
+        att = ref_attacker.Attacker(args, model, wk)
+        quiet(att.prepare_test_data)
+        if tag == "32":
+            out.update(bf_exist=np.asarray(att.exist_edges).reshape(-1, 2),
+                       bf_nonexist=np.asarray(att.nonexist_edges).reshape(-1, 2),
+                       bf_test_nodes=np.asarray(att.test_nodes), bf_n_test=args.n_test)
+        cap = {}
+        att.compute_and_save = lambda e, ne: cap.update(e=np.asarray(e), ne=np.asarray(ne))
+        quiet(att.link_prediction_attack_efficient_balanced)
+        out[f"bf_eff_exist{tag}"], out[f"bf_eff_nonexist{tag}"] = cap["e"], cap["ne"]
+        if tag == "32":
+            for mode in ("baseline", "baseline-feat"):
+                a3 = types.SimpleNamespace(**vars(args))
+                a3.attack_mode = mode
+                att3 = ref_attacker.Attacker(a3, model, wk)
+                att3.test_nodes, att3.exist_edges, att3.nonexist_edges = att.test_nodes, att.exist_edges, att.nonexist_edges
+                cap3 = {}
+                att3.compute_and_save = lambda e, ne: cap3.update(e=np.asarray(e), ne=np.asarray(ne))
+                quiet(att3.baseline_attack_balanced)
+                key = "post" if mode == "baseline" else "attr"
+                out[f"bf_{key}_exist"], out[f"bf_{key}_nonexist"] = cap3["e"], cap3["ne"]
+        # ---- naive on a small unbalanced sample (the method saves by itself: read the file back)
+        a4 = types.SimpleNamespace(sample_type="unbalanced", n_test=T_naive, attack_mode="naive", **base)
+        att4 = ref_attacker.Attacker(a4, model, wk)
+        quiet(att4.prepare_test_data)
+        with tempfile.TemporaryDirectory() as td:
+            cwd = os.getcwd()
+            os.chdir(td)
+            try:
+                quiet(att4.link_prediction_attack)
+                fn = [os.path.join(dp_, f_) for dp_, _, fs in os.walk(td) for f_ in fs][0]
+                saved = torch.load(fn, weights_only=False)
+                if tag == "32":
+                    out["naive_filename"] = os.path.relpath(fn, td)
+            finally:
+                os.chdir(cwd)
+        out[f"naive_pred{tag}"] = np.asarray(saved["result"]["pred"])
+        if tag == "32":
+            out.update(naive_test_nodes=np.asarray(att4.test_nodes), naive_y=np.asarray(saved["result"]["y"]),
+                       naive_exist=np.asarray(att4.exist_edges).reshape(-1, 2),
+                       naive_nonexist=np.asarray(att4.nonexist_edges).reshape(-1, 2))
+    path = os.path.join(HERE, f"{name}.npz")
+    np.savez_compressed(path, **out)
+    print(f"{name}: n={n} edges={len(out['bf_exist'])} nonedges={len(out['bf_nonexist'])} "
+          f"naive pairs={len(out['naive_pred32'])} → {os.path.getsize(path) / 1024:.0f} KiB")
+
+
 if __name__ == "__main__":
     torch.set_num_threads(4)
+    if "--next-only" in sys.argv:
+        run_case_next("tiny_next", "tiny", seed=5, hidden=32)
+        sys.exit(0)
     run_case("tiny_fo", "tiny", seed=0, hidden=32, norm="FirstOrderGCN", sample_type="unbalanced",
              dataset="twitch/ES/RU", T=40)
     run_case("tiny_aug", "tiny", seed=1, hidden=32, norm="AugNormAdj", sample_type="unbalanced-lo",
@@ -183,3 +257,4 @@ if __name__ == "__main__":
              dataset="twitch/ES/RU", T=40, dp="discrete", with_lsa2=False)
     run_case("tiny_lapgraph", "tiny", seed=4, hidden=32, norm="FirstOrderGCN", sample_type="unbalanced",
              dataset="twitch/ES/RU", T=40, dp="continuous", with_lsa2=False)
+    run_case_next("tiny_next", "tiny", seed=5, hidden=32)
