@@ -107,6 +107,14 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+# DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum) per launch of the dominant kernel, from the
+# ncu --set full captures committed under profiles/ (never measured inside a bench run: a run under ncu
+# is not a bench value).  Keyed by (workload, n_gpus, kernel family).
+NCU_TRAFFIC = {
+    ("large", 1, "spmm_ax"): (13.753841e9 + 0.160777e9, "profiles/r1d_ncu_spmm_summary.txt"),
+}
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
@@ -305,9 +313,14 @@ def main():
             dur_ms = per_step[dom] / max(n_launch, 1)
             achieved = alg[dom] / (dur_ms / 1e3) / 1e9
             roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                        "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                        "frac": achieved / peak, "traffic": None, "traffic_source": None, "peak_source": peak_src,
                         "algorithmic_bytes_per_launch": int(alg[dom]), "launch_ms": dur_ms,
                         "share_of_step": per_step[dom] / (ms / args.steps)}
+            hit = NCU_TRAFFIC.get((args.workload, world, dom)) if args.n_test is None else None
+            if hit:
+                roofline["traffic"], roofline["traffic_source"] = hit
+                # the same launch against the bytes it really moves (gathered rows are re-fetched: L2 hit rate 10 %)
+                roofline["dram_frac_of_peak"] = hit[0] / (dur_ms / 1e3) / 1e9 / peak
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
