@@ -104,3 +104,14 @@ def gcn_weights(f: int, h: int, c: int, seed: int = 42):
     w2 = rng.uniform(-s2, s2, (h, c)).astype(np.float32)
     b2 = rng.uniform(-s2, s2, c).astype(np.float32)
     return w1, b1, w2, b2
+
+
+def gcn3_weights(f: int, h1: int, h2: int, c: int, seed: int = 42):
+    """Same distribution for the three GraphConvolution layers of GCN3 (gcn/models.py:28-37)."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for fin, fout in ((f, h1), (h1, h2), (h2, c)):
+        s = 1.0 / np.sqrt(fout)
+        out.append(rng.uniform(-s, s, (fin, fout)).astype(np.float32))
+        out.append(rng.uniform(-s, s, fout).astype(np.float32))
+    return tuple(out)

@@ -140,11 +140,28 @@ def gcn_forward(x, adj, w1, b1, w2, b2):
     return graph_conv(torch.relu(graph_conv(x, adj, w1, b1)), adj, w2, b2)
 
 
+def gcn3_forward(x, adj, w1, b1, w2, b2, w3, b3):
+    """GCN3 (--n-layer 3): gc1 → ReLU → gc2 → ReLU → gc3, raw logits (gcn/models.py:40-46; dropout is
+    the identity in eval)."""
+    x = torch.relu(graph_conv(x, adj, w1, b1))
+    x = torch.relu(graph_conv(x, adj, w2, b2))
+    return graph_conv(x, adj, w3, b3)
+
+
+def model_forward(x, adj, *weights):
+    """GCN for 4 weight arrays, GCN3 for 6 — the two models gcn_trainer.py:81-90 builds for the path."""
+    if len(weights) == 4:
+        return gcn_forward(x, adj, *weights)
+    if len(weights) == 6:
+        return gcn3_forward(x, adj, *weights)
+    raise NotImplementedError(f"n_layer = {len(weights) // 2} not implemented!")   # gcn_trainer.py:88
+
+
 def gcn_forward_np(X, coo, weights, n, dtype=torch.float64):
     row, col, val = coo
     adj = _sparse(row, col, val, n, dtype)
     t = [torch.from_numpy(np.asarray(a)).to(dtype) for a in (X, *weights)]
-    return gcn_forward(t[0], adj, *t[1:]).numpy()
+    return model_forward(t[0], adj, *t[1:]).numpy()
 
 
 # --------------------------------------------------------------------------------------------
@@ -164,7 +181,7 @@ def influence_matrix(X, coo, weights, n, test_nodes, delta, dtype=torch.float64,
     row, col, val = coo
     adj = _sparse(row, col, val, n, dtype)
     x = torch.from_numpy(np.asarray(X)).to(dtype)
-    w1, b1, w2, b2 = [torch.from_numpy(np.asarray(a)).to(dtype) for a in weights]
+    w = [torch.from_numpy(np.asarray(a)).to(dtype) for a in weights]   # 4 arrays: GCN, 6: GCN3
     tn = np.asarray(test_nodes)
     rows = range(len(tn)) if rows is None else rows
     out = np.zeros((len(rows), len(tn)))
@@ -174,10 +191,23 @@ def influence_matrix(X, coo, weights, n, test_nodes, delta, dtype=torch.float64,
             v = int(tn[i])
             pert = torch.zeros_like(x)
             pert[v] = x[v] * delta
-            grad = (gcn_forward(x + pert, adj, w1, b1, w2, b2)
-                    - gcn_forward(x, adj, w1, b1, w2, b2)) / delta
+            grad = (model_forward(x + pert, adj, *w) - model_forward(x, adj, *w)) / delta
             out[k] = grad[sel].norm(dim=1).double().numpy()
     return out
+
+
+def k_hop_support(indptr, indices, test_nodes, hops):
+    """Boolean [T,T]: test_nodes[j] within ``hops`` hops of test_nodes[i] in Â's pattern (a k-layer GCN's
+    influence is bit-exactly 0 outside it: every forward touches the same zeros)."""
+    import scipy.sparse as sp
+    n = len(indptr) - 1
+    tn = np.asarray(test_nodes, dtype=np.int64)
+    A = sp.csr_matrix((np.ones(len(indices), dtype=np.float64), indices, indptr), shape=(n, n))
+    reach = sp.csr_matrix((np.ones(len(tn)), (np.arange(len(tn)), tn)), shape=(len(tn), n))
+    for _ in range(hops):
+        reach = reach @ A
+        reach.data[:] = 1.0
+    return np.asarray(reach[:, tn].todense()) != 0
 
 
 def two_hop_support(indptr, indices, test_nodes):

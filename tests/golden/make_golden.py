@@ -35,7 +35,7 @@ with contextlib.redirect_stdout(io.StringIO()):
     import attacker as ref_attacker  # noqa: E402
     import utils as ref_utils  # noqa: E402
     import worker as ref_worker  # noqa: E402
-    from gcn.models import GCN  # noqa: E402
+    from gcn.models import GCN, GCN3  # noqa: E402
 
 
 def quiet(fn, *a, **k):
@@ -242,8 +242,66 @@ def run_case_next(name, shape, seed, hidden, T_naive=12):
           f"naive pairs={len(out['naive_pred32'])} → {os.path.getsize(path) / 1024:.0f} KiB")
 
 
+def run_case_gcn3(name, shape, seed, h1, h2, T, **override):
+    """--n-layer 3 (GCN3, gcn/models.py:28-46; built by gcn_trainer.py:81-86) under the
+    same efficient attack — the reference's logits, influence matrix (float32 as shipped and float64),
+    pair scores and sklearn metrics."""
+    s = synth.make(shape, seed=seed, hidden=h1, **override)
+    n, f, c = s.n, s.f, s.c
+    weights = synth.gcn3_weights(f, h1, h2, c, seed=42)
+    out = dict(shape=shape, seed=seed, h1=h1, h2=h2, T=T, delta=1e-4, sample_seed=42, norm="FirstOrderGCN",
+               override_keys=np.asarray(sorted(override)), override_vals=np.asarray([override[k] for k in sorted(override)]))
+    adj_ori = ref_graph_reader(s.edges, n, "twitch/ES/RU").tocsr()
+    adj_ori.sort_indices()
+    coo = ref_utils.fetch_normalization("FirstOrderGCN")(adj_ori)
+    adj_t = quiet(ref_utils.sparse_mx_to_torch_sparse_tensor, coo)
+    X = torch.from_numpy(s.features)
+    args = types.SimpleNamespace(dataset="twitch/ES/RU", sample_type="unbalanced", n_test=T, influence=1e-4,
+                                 sample_seed=42, mode="vanilla-clean", attack_mode="efficient", perturb_type=None,
+                                 epsilon=5.0, noise_seed=42, n_layer=3, hidden1=h1, hidden2=h2)
+    keys = ("gc1.weight", "gc1.bias", "gc2.weight", "gc2.bias", "gc3.weight", "gc3.bias")
+    for tag, dbl in (("32", False), ("64", True)):
+        model = quiet(GCN3, f, h1, h2, c, 0.5)
+        model.load_state_dict({k: torch.from_numpy(w) for k, w in zip(keys, weights)})
+        model.eval()
+        if dbl:
+            model = model.double()
+        feats = X.double() if dbl else X
+        adj = adj_t.double() if dbl else adj_t
+        wk = types.SimpleNamespace(n_nodes=n, n_features=f, features=feats, adj_full=adj, features_2=feats,
+                                   adj_2=adj, adj_ori=adj_ori)
+        att = ref_attacker.Attacker(args, model, wk)
+        quiet(att.prepare_test_data)
+        tn = np.asarray(att.test_nodes)
+        if tag == "32":
+            out.update(test_nodes=tn, exist=np.asarray(att.exist_edges).reshape(-1, 2),
+                       nonexist=np.asarray(att.nonexist_edges).reshape(-1, 2))
+            with torch.no_grad():
+                out["logits"] = model(feats, adj).numpy()
+        infl = np.zeros((T, T))
+        with torch.no_grad():
+            for i in range(T):
+                g = att.get_gradient_eps_mat(tn[i])
+                for j in range(T):
+                    infl[i][j] = g[tn[j]].norm().item()
+        out[f"influence{tag}"] = infl
+        cap = {}
+        att.compute_and_save = lambda e, ne: cap.update(e=np.asarray(e), ne=np.asarray(ne))
+        quiet(att.link_prediction_attack_efficient)
+        out[f"score_exist{tag}"], out[f"score_nonexist{tag}"] = cap["e"], cap["ne"]
+    path = os.path.join(HERE, f"{name}.npz")
+    np.savez_compressed(path, **out)
+    nz = int((out["influence64"] != 0).sum())
+    print(f"{name}: n={n} T={T} h1={h1} h2={h2} non-zero influence entries {nz}/{T * T} → "
+          f"{os.path.getsize(path) / 1024:.0f} KiB")
+
+
 if __name__ == "__main__":
     torch.set_num_threads(4)
+    if "--gcn3-only" in sys.argv:
+        run_case_gcn3("tiny_gcn3", "tiny", seed=6, h1=32, h2=16, T=40)
+        run_case_gcn3("sparse_gcn3", "small", seed=7, h1=32, h2=24, T=120, m=1800)
+        sys.exit(0)
     if "--next-only" in sys.argv:
         run_case_next("tiny_next", "tiny", seed=5, hidden=32)
         sys.exit(0)
@@ -258,3 +316,5 @@ if __name__ == "__main__":
     run_case("tiny_lapgraph", "tiny", seed=4, hidden=32, norm="FirstOrderGCN", sample_type="unbalanced",
              dataset="twitch/ES/RU", T=40, dp="continuous", with_lsa2=False)
     run_case_next("tiny_next", "tiny", seed=5, hidden=32)
+    run_case_gcn3("tiny_gcn3", "tiny", seed=6, h1=32, h2=16, T=40)
+    run_case_gcn3("sparse_gcn3", "small", seed=7, h1=32, h2=24, T=120, m=1800)
