@@ -145,6 +145,25 @@ int lt_attack_efficient(const int32_t* indptr, const int32_t* indices, const flo
                         int32_t lo, int32_t hi, float delta, float* out, int64_t ldo,
                         int64_t* info_host /* nullable, 8 entries as lt_plan_info */, lt_stream_t stream);
 
+/* f3  --n-layer 3: GCN3.forward (gcn/models.py:40-46, eval mode) and the efficient attack on it
+ *     (gcn_trainer.py:81-86 builds GCN3(nfeat, hidden1, hidden2, nclass); Attacker calls self.model
+ *     generically, attacker.py:100-108).  W1 [f,h1], W2 [h1,h2], W3 [h2,c] row-major.
+ *     lt_attack_efficient3: out[j,i] as lt_attack_efficient, exactly 0 outside THREE hops.  The perturbed
+ *     nodes are processed in chunks whose second-hop expansions (Σ_{r∈N̂(v)} nnz(Â[r,:]) records) stay below
+ *     max_chunk_records (<= 0: sized from the free device memory).  info_host (nullable, 8 entries):
+ *     chunks, first-hop incidences, second-hop records, second-hop incidences, third-hop records,
+ *     pairs in the support, 0, 0.  Synchronises several times per chunk. */
+int lt_gcn3_forward(const int32_t* indptr, const int32_t* indices, const float* values, int32_t n,
+                    const float* X, int64_t ldx, int32_t f, const float* W1, const float* b1,
+                    const float* W2, const float* b2, const float* W3, const float* b3, int32_t h1,
+                    int32_t h2, int32_t c, float* logits, int64_t ldz, lt_stream_t stream);
+int lt_attack_efficient3(const int32_t* indptr, const int32_t* indices, const float* values, int32_t n,
+                         const float* X, int64_t ldx, int32_t f, const float* W1, const float* b1,
+                         const float* W2, const float* b2, const float* W3, int32_t h1, int32_t h2,
+                         int32_t c, const int32_t* test_nodes, int32_t T, int32_t lo, int32_t hi,
+                         float delta, float* out, int64_t ldo, int64_t max_chunk_records,
+                         int64_t* info_host, lt_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * a6  _get_edge_sets_among_nodes, utils/load.py:304-326: label of every pair i<j in sample order
  *     (row-major) = test_nodes[j] ∈ row test_nodes[i] of adj_ori.  labels: uint8 [T(T-1)/2].

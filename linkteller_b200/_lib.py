@@ -42,6 +42,9 @@ _SIGS = {
     "lt_plan_copy_rows": [P, P, P],
     "lt_influence_rows": [P, P, I64, P, I64, P, P, I32, I32, F32, P, I64, P],
     "lt_attack_efficient": [P, P, P, I32, P, I64, I32, P, P, P, I32, I32, P, I32, I32, I32, F32, P, I64, P, P],
+    "lt_gcn3_forward": [P, P, P, I32, P, I64, I32, P, P, P, P, P, P, I32, I32, I32, P, I64, P],
+    "lt_attack_efficient3": [P, P, P, I32, P, I64, I32, P, P, P, P, P, I32, I32, I32, P, I32, I32, I32, F32, P, I64, I64,
+                             P, P],
     "lt_pair_labels": [P, P, I32, P, I32, P, P, P],
     "lt_pair_scores": [P, I64, I32, P, P],
     "lt_auc_ap": [P, P, I64, P, P, P],

@@ -47,6 +47,24 @@ def influence_matrix(adj_hat: ops.DeviceCSR, x, w1, b1, w2, test_nodes: torch.Te
     return out
 
 
+def influence_matrix_model(adj_hat: ops.DeviceCSR, x, weights, test_nodes: torch.Tensor, delta: float,
+                           group=None, out: Optional[torch.Tensor] = None):
+    """influence_matrix for the model the weights belong to: 4 tensors (w1,b1,w2,b2) → GCN, 6 → GCN3
+    (--n-layer 3).  Same sharding: rank g owns a contiguous slice of the perturbed nodes."""
+    T = test_nodes.numel()
+    world, rank = 1, 0
+    if group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+        world = torch.distributed.get_world_size(group)
+        rank = torch.distributed.get_rank(group)
+    if out is None:
+        out = torch.empty((T, T), dtype=torch.float32, device=x.device)
+    lo, hi = slice_bounds(T, world, rank)
+    ops.attack_rows(adj_hat, x, weights, test_nodes, delta, lo=lo, hi=hi, out=out[lo:hi])
+    if world > 1:
+        gather_rows(out, T, world, group)
+    return out
+
+
 def gather_rows(out: torch.Tensor, T: int, world: int, group=None):
     """All-gather the row slices in place.  Equal slices use one all_gather_into_tensor on the
     output buffer itself; ragged slices (T % world != 0) fall back to per-rank broadcasts."""

@@ -8,7 +8,8 @@ result file name and dict schema.  What changes is where the work happens:
   prepare_test_data   node sampling stays on numpy's legacy stream (same seed ⇒ same nodes); the
                       O(T²·deg) Python pair enumeration (utils/load.py:304-326) becomes lt_pair_labels
   efficient attack    the T x 2 full GCN forwards + T² `.item()` calls (attacker.py:220-229) become
-                      one lt_attack_efficient call (frontier propagation, csrc/frontier.cu)
+                      one lt_attack_efficient call (frontier propagation, csrc/frontier.cu);
+                      lt_attack_efficient3 when the model is GCN3 (--n-layer 3)
   baseline attacks    the T² Python loop of torch expressions (attacker.py:311-316) becomes lt_lsa2_corr
   compute_and_save    sklearn's sort-based curves become lt_rank_curve / lt_auc_ap on the device
 
@@ -113,12 +114,14 @@ class Attacker:
             hat = _adj.device_csr_of(self.adj, self.device)
             sd = {k: v.detach().to(device=self.device, dtype=torch.float32).contiguous()
                   for k, v in self.model.state_dict().items()}
-            need = ("gc1.weight", "gc1.bias", "gc2.weight", "gc2.bias")
-            if any(k not in sd for k in need):
-                raise NotImplementedError("the accelerated attack covers the 2-layer GCN (gcn/models.py:8-25); "
+            need = ["gc1.weight", "gc1.bias", "gc2.weight", "gc2.bias"]
+            if "gc3.weight" in sd:                   # --n-layer 3: GCN3 (gcn/models.py:28-46)
+                need += ["gc3.weight", "gc3.bias"]
+            if any(k not in sd for k in need) or len(sd) != len(need):
+                raise NotImplementedError("the accelerated attack covers GCN and GCN3 (gcn/models.py:8-46); "
                                           f"model has parameters {sorted(sd)}")
             self._dev = dict(x=x, hat=hat, w1=sd["gc1.weight"], b1=sd["gc1.bias"], w2=sd["gc2.weight"],
-                             b2=sd["gc2.bias"])
+                             b2=sd["gc2.bias"], weights=tuple(sd[k] for k in need))
         return self._dev
 
     def _adj_ori_device(self):
@@ -210,8 +213,8 @@ class Attacker:
         delta = float(self.args.influence)
         xp = d["x"].clone()
         xp[v] += d["x"][v] * delta
-        f1 = ops.gcn_forward(d["hat"], xp, d["w1"], d["b1"], d["w2"], d["b2"])
-        f0 = ops.gcn_forward(d["hat"], d["x"], d["w1"], d["b1"], d["w2"], d["b2"])
+        f1 = ops.model_forward(d["hat"], xp, d["weights"])
+        f0 = ops.model_forward(d["hat"], d["x"], d["weights"])
         return (f1 - f0) / delta
 
     # ------------------------------------------------------------------ a8
@@ -219,8 +222,8 @@ class Attacker:
         """influence_val of attacker.py:216-229 as a float32 [T,T] device tensor."""
         d = self._staged()
         tn = torch.from_numpy(np.asarray(self.test_nodes).astype(np.int32)).to(self.device)
-        return attack.influence_matrix(d["hat"], d["x"], d["w1"], d["b1"], d["w2"], tn, float(self.args.influence),
-                                       group=self.group)
+        return attack.influence_matrix_model(d["hat"], d["x"], d["weights"], tn, float(self.args.influence),
+                                             group=self.group)
 
     def link_prediction_attack_efficient(self):
         t = time.time()
@@ -241,7 +244,9 @@ class Attacker:
         d = self._staged()
         u, v = self._pair_tensors(prs)
         p, o = (u, v) if perturb_first else (v, u)
-        sc = ops.pair_influence(d["hat"], d["x"], d["w1"], d["b1"], d["w2"], p, o, float(self.args.influence))
+        w = d["weights"]
+        sc = ops.pair_influence(d["hat"], d["x"], d["w1"], d["b1"], d["w2"], p, o, float(self.args.influence),
+                                b2=d["b2"] if len(w) == 6 else None, w3=w[4] if len(w) == 6 else None)
         return sc.cpu().numpy().astype(np.float64)
 
     def link_prediction_attack_efficient_balanced(self):
@@ -290,7 +295,7 @@ class Attacker:
         d = self._staged()
         mode = self.args.attack_mode
         if mode == 'baseline':
-            mat = ops.gcn_forward(d["hat"], d["x"], d["w1"], d["b1"], d["w2"], d["b2"])
+            mat = ops.model_forward(d["hat"], d["x"], d["weights"])
             tr = "sigmoid" if self.dataset == 'ppi' else "softmax"
         elif mode == 'baseline-feat':
             mat, tr = d["x"], "none"
@@ -311,7 +316,7 @@ class Attacker:
         mode = self.args.attack_mode
         tn = torch.from_numpy(np.asarray(self.test_nodes).astype(np.int32)).to(self.device)
         if mode == 'baseline':
-            logits = ops.gcn_forward(d["hat"], d["x"], d["w1"], d["b1"], d["w2"], d["b2"])
+            logits = ops.model_forward(d["hat"], d["x"], d["weights"])
             dist = ops.lsa2_corr(logits, tn, "sigmoid" if self.dataset == 'ppi' else "softmax")   # attacker.py:296-299
         elif mode == 'baseline-feat':
             dist = ops.lsa2_corr(d["x"], tn, "none")

@@ -19,6 +19,8 @@
 //   F2 k_frontier_reduce : out[j,i] = ‖Σ_k w_k·ΔQ[e_k,:]‖₂  (segmented, deterministic)
 #include "gemm_tc.cuh"
 
+#include <stdlib.h>
+
 namespace lt {
 
 int gemm_f32(const float* A, int64_t lda, const int32_t* a_rows, const float* B, int64_t ldb, int transB,
@@ -143,7 +145,7 @@ __global__ void k_observers(const int32_t* __restrict__ indptr, const int32_t* _
     if (t >= all_off[T]) return;
     const int32_t i = (int32_t)upper_bound(all_off, 0, (int64_t)T + 1, (int32_t)t) - 1;
     const int32_t k = indptr[test_nodes[i]] + ((int32_t)t - all_off[i]);
-    const int32_t rho = rmap[indices[k]];
+    const int32_t rho = rmap ? rmap[indices[k]] : indices[k];   // no map: observer lists over all n nodes
     if (rho < 0) return;
     if (MODE == 0) {
         atomicAdd(&cnt_or_cursor[rho], 1);
@@ -553,23 +555,28 @@ static int plan_build(lt_plan* p, const int32_t* indptr, const int32_t* indices,
     return LT_OK;
 }
 
-int influence_rows(const lt_plan* p, const float* H_R, int64_t ldh, const float* P, int64_t ldp,
-                   const int32_t* p_index, const float* W2, int32_t h, int32_t c, float delta, float* out,
-                   int64_t ldo, cudaStream_t s) {
-    const int64_t E = p->E, M = p->M;
-    LT_CUDA(cudaMemset2DAsync(out, (size_t)ldo * 4, 0, (size_t)p->T * 4, (size_t)p->Ts, s));
-    if (E == 0 || M == 0) return LT_OK;
-    if (h % 4 != 0 || ldh % 4 != 0 || ldp % 4 != 0 || (uintptr_t)H_R % 16 || (uintptr_t)P % 16) {
+// ΔQ[e,:] = ΔR[e,:]·W for every incidence e of the plan (F1).  H row of incidence e = H[h_index[e]]
+// (the plan's compact frontier index by default; node ids when H holds every row), P row = P[p_index ? p_index[j] : j].
+// dq: [E, lddq] with lddq = frontier_lddq(E, h, c).
+static inline bool frontier_use_tc(int64_t E, int32_t h, int32_t c) {
+    return c <= 256 && c >= 8 && E * (int64_t)h * c >= ((int64_t)1 << 24);
+}
+static inline int32_t frontier_lddq(int64_t E, int32_t h, int32_t c) { return frontier_use_tc(E, h, c) ? (c + 3) / 4 * 4 : c; }
+
+static int frontier_dq(const lt_plan* p, const int32_t* h_index, const float* H, int64_t ldh, const float* P, int64_t ldp,
+                       const int32_t* p_index, const float* W2, int32_t h, int32_t c, float delta, float* dq,
+                       cudaStream_t s) {
+    const int64_t E = p->E;
+    if (E == 0) return LT_OK;
+    if (h % 4 != 0 || ldh % 4 != 0 || ldp % 4 != 0 || (uintptr_t)H % 16 || (uintptr_t)P % 16) {
         set_error("lt_influence_rows: h, ldh, ldp must be multiples of 4 and H_R, P 16-byte aligned");
         return LT_ERR_ARG;
     }
     Scratch scratch(s);
-    float* dq;
     const float inv_delta = 1.0f / delta;
     // ΔQ = ΔR·W2: on the tensor cores (3xTF32, tcgen05) when the product is large enough, else fp32 SIMT
-    const bool use_tc = c <= 256 && c >= 8 && E * (int64_t)h * c >= ((int64_t)1 << 24);
-    const int32_t lddq = use_tc ? (c + 3) / 4 * 4 : c;
-    LT_TRY(scratch.alloc(&dq, (size_t)E * lddq));
+    const bool use_tc = frontier_use_tc(E, h, c);
+    const int32_t lddq = frontier_lddq(E, h, c);
     if (use_tc) {
         ProfScope prof("frontier_dq", s);
         const int nt = tc_pick_nt(c);
@@ -577,7 +584,7 @@ int influence_rows(const lt_plan* p, const float* H_R, int64_t ldh, const float*
         uint32_t* img;
         LT_TRY(scratch.alloc(&img, (size_t)kchunks * 2 * n_pad * TC_BK));
         LT_TRY(tc_prepack_b(W2, c, 0, c, h, n_pad, img, s));
-        const DeltaRProd prod{p->s_j, p->s_rho, p->s_a, p_index, H_R, ldh, P, ldp, delta, inv_delta};
+        const DeltaRProd prod{p->s_j, h_index, p->s_a, p_index, H, ldh, P, ldp, delta, inv_delta};
         switch (nt) {
             case 32: LT_TRY((launch_tc<32, 2>(prod, img, nullptr, 0, dq, lddq, (int32_t)E, c, h, n_pad, kchunks, s))); break;
             case 48: LT_TRY((launch_tc<48, 2>(prod, img, nullptr, 0, dq, lddq, (int32_t)E, c, h, n_pad, kchunks, s))); break;
@@ -585,7 +592,8 @@ int influence_rows(const lt_plan* p, const float* H_R, int64_t ldh, const float*
             case 128: LT_TRY((launch_tc<128, 1>(prod, img, nullptr, 0, dq, lddq, (int32_t)E, c, h, n_pad, kchunks, s))); break;
             default: LT_TRY((launch_tc<256, 1>(prod, img, nullptr, 0, dq, lddq, (int32_t)E, c, h, n_pad, kchunks, s))); break;
         }
-    } else {
+        return LT_OK;
+    }
     const unsigned bl = (unsigned)ceil_div(E, F1_TILE_E);
     for (int32_t c0 = 0; c0 < c; c0 += 128) {
         ProfScope prof("frontier_dq", s);
@@ -595,7 +603,7 @@ int influence_rows(const lt_plan* p, const float* H_R, int64_t ldh, const float*
 #define LT_F1(NC_)                                                                                             \
     do {                                                                                                       \
         LT_CUDA(cudaFuncSetAttribute(k_frontier_dq<NC_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        k_frontier_dq<NC_><<<bl, F1_THREADS, smem, s>>>(p->s_j, p->s_rho, p->s_a, E, H_R, ldh, P, ldp, p_index, W2, h, \
+        k_frontier_dq<NC_><<<bl, F1_THREADS, smem, s>>>(p->s_j, h_index, p->s_a, E, H, ldh, P, ldp, p_index, W2, h,  \
                                                         c, c0, delta, inv_delta, dq);                          \
     } while (0)
         if (nc == 1) LT_F1(1);
@@ -605,11 +613,17 @@ int influence_rows(const lt_plan* p, const float* H_R, int64_t ldh, const float*
 #undef LT_F1
         LT_LAUNCH_CHECK();
     }
-    }
+    return LT_OK;
+}
+
+// out[j,i] = ‖Σ_k w_k·ΔQ[e_k,:]‖₂ for every group of sorted records (F2)
+static int frontier_reduce(const uint64_t* rec_key, const uint64_t* rec_val, const int32_t* grp_off, const int32_t* n_groups,
+                           const int32_t* big, const int32_t* n_big, int64_t M, const float* dq, int32_t lddq, int32_t c,
+                           float* out, int64_t ldo, cudaStream_t s) {
+    if (M == 0) return LT_OK;
     ProfScope prof2("frontier_reduce", s);
 #define LT_F2(G_)                                                                                              \
-    k_frontier_reduce<G_><<<(unsigned)ceil_div(M * G_, 256), 256, 0, s>>>(p->rec_key, p->rec_val, p->grp_off,  \
-                                                                          p->n_groups, dq, lddq, c, out, ldo)
+    k_frontier_reduce<G_><<<(unsigned)ceil_div(M * G_, 256), 256, 0, s>>>(rec_key, rec_val, grp_off, n_groups, dq, lddq, c, out, ldo)
     if (c <= 1) LT_F2(1);
     else if (c <= 2) LT_F2(2);
     else if (c <= 4) LT_F2(4);
@@ -619,11 +633,25 @@ int influence_rows(const lt_plan* p, const float* H_R, int64_t ldh, const float*
 #undef LT_F2
     LT_LAUNCH_CHECK();
     if (M > F2_BIG) {
-        k_frontier_reduce_big<<<(unsigned)num_sms() * 2, 32 * F2_BIG_WARPS, 0, s>>>(p->rec_key, p->rec_val, p->grp_off, p->big, p->n_big,
-                                                                     dq, lddq, c, out, ldo);
+        k_frontier_reduce_big<<<(unsigned)num_sms() * 2, 32 * F2_BIG_WARPS, 0, s>>>(rec_key, rec_val, grp_off, big, n_big, dq, lddq, c,
+                                                                                    out, ldo);
         LT_LAUNCH_CHECK();
     }
     return LT_OK;
+}
+
+int influence_rows(const lt_plan* p, const float* H_R, int64_t ldh, const float* P, int64_t ldp,
+                   const int32_t* p_index, const float* W2, int32_t h, int32_t c, float delta, float* out,
+                   int64_t ldo, cudaStream_t s) {
+    const int64_t E = p->E, M = p->M;
+    LT_CUDA(cudaMemset2DAsync(out, (size_t)ldo * 4, 0, (size_t)p->T * 4, (size_t)p->Ts, s));
+    if (E == 0 || M == 0) return LT_OK;
+    Scratch scratch(s);
+    float* dq;
+    const int32_t lddq = frontier_lddq(E, h, c);
+    LT_TRY(scratch.alloc(&dq, (size_t)E * lddq));
+    LT_TRY(frontier_dq(p, p->s_rho, H_R, ldh, P, ldp, p_index, W2, h, c, delta, dq, s));
+    return frontier_reduce(p->rec_key, p->rec_val, p->grp_off, p->n_groups, p->big, p->n_big, M, dq, lddq, c, out, ldo, s);
 }
 
 static void plan_info(const lt_plan* p, int32_t h, int32_t c, int64_t* info) {
@@ -638,6 +666,325 @@ static void plan_info(const lt_plan* p, int32_t h, int32_t c, int64_t* info) {
               (int64_t)p->Ts * p->T * 4;
     info[6] = p->nnzR;
     info[7] = 0;
+}
+
+
+// ==================================================================================== three layers (GCN3)
+// --n-layer 3 (gcn/models.py:28-46, built by gcn_trainer.py:81-86) under the same efficient attack.
+// With H1 = Â·X·W1 + b1, H2 = Â·relu(H1)·W2 + b2 (both kept for every node) the perturbation of x_v moves
+//     layer 1 on N̂(v):    ΔR1[r] exactly as in the two-layer model,            ΔQ1[r] = ΔR1[r]·W2
+//     layer 2 on N̂²(v):   ΔH2[s] = Σ_{r ∈ N̂(v) ∩ N̂(s)} Â[s,r]·ΔQ1[r],  ΔR2[s] = (relu(H2[s] + δ·ΔH2[s]) − relu(H2[s]))/δ
+//                          (evaluated case by case on the signs, so nothing cancels),   ΔQ2[s] = ΔR2[s]·W3
+//     logits on N̂³(v):    ΔZ[u] = Σ_{s ∈ N̂²(v) ∩ N̂(u)} Â[u,s]·ΔQ2[s],   influence = ‖ΔZ[u]‖₂ for the test nodes u.
+// Stage 1 is the two-layer plan's incidence list S and F1.  Stage 2 expands every incidence (j,r) over row r
+// into records keyed (j,s), radix-sorts them (stable: contributions stay in ascending r) and reduces each
+// group against one H2 row.  Stage 3 is F2 over the (j,s) incidences with observer lists for all n nodes.
+// The perturbed nodes are processed in chunks sized so that the stage-2 records fit the memory budget.
+
+__global__ void k3_relu_copy(const float4* __restrict__ src, float4* __restrict__ dst, int64_t count4) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count4) return;
+    float4 v = src[i];
+    v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+    dst[i] = v;
+}
+
+// cost[j] = Σ_{r ∈ N̂(v_j)} nnz(Â[r,:]) = stage-2 records of perturbed node j; one warp per node of the slice
+__global__ void k3_costs(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                         const int32_t* __restrict__ test_nodes, int32_t lo, int32_t Ts, int32_t n, int64_t* __restrict__ cost) {
+    const int lane = threadIdx.x & 31;
+    const int64_t j = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (j >= Ts) return;
+    const int32_t v = test_nodes[lo + j];
+    int64_t acc = 0;
+    if (v >= 0 && v < n)
+        for (int32_t k = indptr[v] + lane; k < indptr[v + 1]; k += 32) {
+            const int32_t r = indices[k];
+            acc += indptr[r + 1] - indptr[r];
+        }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(LT_FULL, acc, o);
+    if (lane == 0) cost[j] = acc;
+}
+
+// per incidence: node id of its frontier row and the length of that row
+__global__ void k3_inc_rows(const int32_t* __restrict__ s_rho, const int32_t* __restrict__ rows, int64_t E,
+                            const int32_t* __restrict__ indptr, int32_t* __restrict__ s_node, int32_t* __restrict__ len) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    const int32_t r = rows[s_rho[e]];
+    s_node[e] = r;
+    len[e] = indptr[r + 1] - indptr[r];
+}
+
+// one thread per stage-2 record m: incidence e = (j,r) owning it (binary search in off), s = its (m − off[e])-th
+// neighbour of r, w = Â[s,r] looked up in row s (the value the layer-2 spmm multiplies ΔQ1[r] with)
+__global__ void k3_expand(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                          const float* __restrict__ values, const int32_t* __restrict__ s_j,
+                          const int32_t* __restrict__ s_node, const int64_t* __restrict__ off, int64_t E, int64_t M,
+                          uint64_t* __restrict__ key, uint64_t* __restrict__ val, int* __restrict__ err) {
+    const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    const int64_t e = upper_bound(off, 0, E + 1, m) - 1;
+    const int32_t r = s_node[e];
+    const int32_t sn = indices[indptr[r] + (int32_t)(m - off[e])];
+    const int32_t sb = indptr[sn], se = indptr[sn + 1];
+    const int64_t p = lower_bound(indices, (int64_t)sb, (int64_t)se, r);
+    float w = 0.f;
+    if (p < se && indices[p] == r) w = values[p];
+    else atomicOr(err, 4);
+    key[m] = ((uint64_t)(uint32_t)s_j[e] << 32) | (uint32_t)sn;
+    val[m] = ((uint64_t)(uint32_t)e << 32) | (uint64_t)__float_as_uint(w);
+}
+
+// one warp per group g = (j,s): ΔH2 = Σ w·ΔQ1[e,:] in record order, ΔR2 against H2[s]; lanes ↔ columns
+__global__ void __launch_bounds__(256)
+k3_middle(const uint64_t* __restrict__ key, const uint64_t* __restrict__ val, const int32_t* __restrict__ grp_off,
+          const int32_t* __restrict__ n_groups, const float* __restrict__ dq1, int32_t lddq1,
+          const float* __restrict__ H2, int64_t ldh2, int32_t h2, float delta, float inv_delta,
+          float* __restrict__ dr2, int64_t lddr2, int32_t* __restrict__ e2_j, int32_t* __restrict__ e2_s) {
+    const int lane = threadIdx.x & 31;
+    const int64_t g = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (g >= *n_groups) return;
+    const int32_t m0 = grp_off[g], m1 = grp_off[g + 1];
+    const uint64_t k0 = key[m0];
+    const int32_t sn = (int32_t)(k0 & 0xffffffffu);
+    if (lane == 0) { e2_j[g] = (int32_t)(k0 >> 32); e2_s[g] = sn; }
+    for (int col = lane; col < h2; col += 32) {
+        const float z = f2_column(val, dq1, lddq1, col, m0, m1);
+        const float hh = H2[(int64_t)sn * ldh2 + col];
+        const float hp = fmaf(delta, z, hh);               // H2'[s,col]
+        float d;
+        if (hh > 0.f) d = hp > 0.f ? z : -hh * inv_delta;
+        else d = hp > 0.f ? hp * inv_delta : 0.f;
+        dr2[g * lddr2 + col] = d;
+    }
+}
+
+struct Gcn3Info { int64_t chunks = 0, E1 = 0, M2 = 0, E2 = 0, M3 = 0, pairs = 0; };
+
+// sorted records → group offsets (+ list of big groups when `big` is given); returns nothing on the host
+static int group_records(const uint64_t* key, int64_t M, int32_t* grp_off, int32_t* n_groups, int32_t* big, int32_t* n_big,
+                         Scratch& scratch, cudaStream_t s) {
+    int32_t* head;
+    LT_TRY(scratch.alloc(&head, (size_t)M + 1));
+    LT_CUDA(cudaMemsetAsync(n_groups, 0, 4, s));
+    k_rec_heads<<<(unsigned)ceil_div(M, 256), 256, 0, s>>>(key, M, head);
+    LT_LAUNCH_CHECK();
+    LT_TRY(exclusive_scan_i32(head, head, M, s));
+    k_group_offsets<<<(unsigned)ceil_div(M + 1, 256), 256, 0, s>>>(head, M, grp_off, n_groups);
+    LT_LAUNCH_CHECK();
+    if (big) {
+        LT_CUDA(cudaMemsetAsync(n_big, 0, 4, s));
+        k_big_groups<<<(unsigned)ceil_div(M, 256), 256, 0, s>>>(grp_off, n_groups, big, n_big);
+        LT_LAUNCH_CHECK();
+    }
+    return LT_OK;
+}
+
+// influence rows of the perturbed nodes test_nodes[lo:hi) for one chunk; out → row lo of the caller's block
+static int gcn3_chunk(const int32_t* indptr, const int32_t* indices, const float* values, int32_t n,
+                      const int32_t* test_nodes, int32_t T, int32_t lo, int32_t hi, const float* P, const float* H1,
+                      int64_t ld1, const float* H2, int64_t ld2, const float* W2, const float* W3, int32_t h1, int32_t h2,
+                      int32_t c, const int32_t* b_indptr, const int32_t* b_i, const float* b_w, float delta, float* out,
+                      int64_t ldo, Gcn3Info* info, cudaStream_t s) {
+    const int32_t Ts = hi - lo;
+    LT_CUDA(cudaMemset2DAsync(out, (size_t)ldo * 4, 0, (size_t)T * 4, (size_t)Ts, s));
+    lt_plan* plan = nullptr;
+    LT_TRY(lt_plan_create(indptr, indices, values, n, test_nodes, T, lo, hi, (lt_stream_t)s, &plan));
+    struct PlanGuard { lt_plan* p; cudaStream_t s; ~PlanGuard() { lt_plan_destroy(p, (lt_stream_t)s); } } guard{plan, s};
+    const int64_t E1 = plan->E;
+    if (E1 == 0) return LT_OK;
+    Scratch scratch(s);
+    const float inv_delta = 1.0f / delta;
+
+    // ---- stage 1: ΔQ1 = ΔR1·W2 per incidence (j,r)
+    int32_t *s_node, *len1;
+    int64_t* off2;
+    float* dq1;
+    const int32_t lddq1 = frontier_lddq(E1, h1, h2);
+    LT_TRY(scratch.alloc(&s_node, (size_t)E1));
+    LT_TRY(scratch.alloc(&len1, (size_t)E1 + 1));
+    LT_TRY(scratch.alloc(&off2, (size_t)E1 + 1));
+    LT_TRY(scratch.alloc(&dq1, (size_t)E1 * lddq1));
+    k3_inc_rows<<<(unsigned)ceil_div(E1, 256), 256, 0, s>>>(plan->s_rho, plan->rows, E1, indptr, s_node, len1);
+    LT_LAUNCH_CHECK();
+    LT_TRY(exclusive_scan_i32_to_i64(len1, off2, E1, s));
+    LT_TRY(frontier_dq(plan, s_node, H1, ld1, P, ld1, test_nodes + lo, W2, h1, h2, delta, dq1, s));
+    int64_t M2 = 0;
+    LT_CUDA(cudaMemcpyAsync(&M2, off2 + E1, 8, cudaMemcpyDeviceToHost, s));
+    LT_CUDA(cudaStreamSynchronize(s));
+    if (M2 >= ((int64_t)1 << 31)) { set_error("lt_attack_efficient3: %lld stage-2 records in one chunk exceed 2^31", (long long)M2); return LT_ERR_CAPACITY; }
+    if (M2 == 0) return LT_OK;
+
+    // ---- stage 2: records (j,s) ← (e, Â[s,r]); sort; ΔR2 per group; ΔQ2 = ΔR2·W3
+    uint64_t *key2, *val2;
+    int32_t *grp2, *ng2;
+    int* err;
+    LT_TRY(scratch.alloc(&key2, (size_t)M2));
+    LT_TRY(scratch.alloc(&val2, (size_t)M2));
+    LT_TRY(scratch.alloc(&grp2, (size_t)M2 + 2));
+    LT_TRY(scratch.alloc(&ng2, 1));
+    LT_TRY(scratch.alloc(&err, 1));
+    LT_CUDA(cudaMemsetAsync(err, 0, sizeof(int), s));
+    {
+        ProfScope prof("gcn3_plan2", s);
+        k3_expand<<<(unsigned)ceil_div(M2, 256), 256, 0, s>>>(indptr, indices, values, plan->s_j, s_node, off2, E1, M2, key2, val2, err);
+        LT_LAUNCH_CHECK();
+        BitRange ranges[2] = {{0, bits_for((uint64_t)(n - 1))}, {32, 32 + bits_for((uint64_t)(Ts > 1 ? Ts - 1 : 1))}};
+        LT_TRY(radix_sort_u64(key2, val2, M2, ranges, Ts > 1 ? 2 : 1, s));
+        LT_TRY(group_records(key2, M2, grp2, ng2, nullptr, nullptr, scratch, s));
+    }
+    int32_t E2 = 0;
+    int herr = 0;
+    LT_CUDA(cudaMemcpyAsync(&E2, ng2, 4, cudaMemcpyDeviceToHost, s));
+    LT_CUDA(cudaMemcpyAsync(&herr, err, sizeof(int), cudaMemcpyDeviceToHost, s));
+    LT_CUDA(cudaStreamSynchronize(s));
+    if (herr & 4) {
+        set_error("lt_attack_efficient3: Â[s,r] missing for a stored Â[r,s] — the adjacency pattern is not symmetric");
+        return LT_ERR_DATA;
+    }
+    float *dr2, *dq2;
+    int32_t *e2_j, *e2_s, *rc3;
+    int64_t* off3;
+    const int64_t lddr2 = (h2 + 3) / 4 * 4;
+    LT_TRY(scratch.alloc(&dr2, (size_t)E2 * lddr2));
+    LT_TRY(scratch.alloc(&dq2, (size_t)E2 * c));
+    LT_TRY(scratch.alloc(&e2_j, (size_t)E2));
+    LT_TRY(scratch.alloc(&e2_s, (size_t)E2));
+    LT_TRY(scratch.alloc(&rc3, (size_t)E2 + 1));
+    LT_TRY(scratch.alloc(&off3, (size_t)E2 + 1));
+    {
+        ProfScope prof("gcn3_middle", s);
+        if (lddr2 != h2) LT_CUDA(cudaMemsetAsync(dr2, 0, (size_t)E2 * lddr2 * 4, s));
+        k3_middle<<<(unsigned)ceil_div((int64_t)E2 * 32, 256), 256, 0, s>>>(key2, val2, grp2, ng2, dq1, lddq1, H2, ld2, h2, delta,
+                                                                           inv_delta, dr2, lddr2, e2_j, e2_s);
+        LT_LAUNCH_CHECK();
+    }
+    {
+        ProfScope prof("gcn3_gemm_q2", s);
+        LT_TRY(gemm_f32(dr2, lddr2, nullptr, W3, c, 0, nullptr, 0, dq2, c, E2, c, h2, 0, s));
+    }
+
+    // ---- stage 3: records (j,i) ← (e2, Â[u_i,s]) from the observer lists; sort; 2-norm per output pair
+    k_rec_counts<<<(unsigned)ceil_div(E2, 256), 256, 0, s>>>(e2_s, E2, b_indptr, rc3);
+    LT_LAUNCH_CHECK();
+    LT_TRY(exclusive_scan_i32_to_i64(rc3, off3, E2, s));
+    int64_t M3 = 0;
+    LT_CUDA(cudaMemcpyAsync(&M3, off3 + E2, 8, cudaMemcpyDeviceToHost, s));
+    LT_CUDA(cudaStreamSynchronize(s));
+    if (M3 >= ((int64_t)1 << 31)) { set_error("lt_attack_efficient3: %lld stage-3 records in one chunk exceed 2^31", (long long)M3); return LT_ERR_CAPACITY; }
+    info->chunks += 1; info->E1 += E1; info->M2 += M2; info->E2 += E2; info->M3 += M3;
+    if (M3 == 0) return LT_OK;
+    uint64_t *key3, *val3;
+    int32_t *grp3, *ng3, *big3, *nbig3;
+    LT_TRY(scratch.alloc(&key3, (size_t)M3));
+    LT_TRY(scratch.alloc(&val3, (size_t)M3));
+    LT_TRY(scratch.alloc(&grp3, (size_t)M3 + 2));
+    LT_TRY(scratch.alloc(&ng3, 1));
+    LT_TRY(scratch.alloc(&big3, (size_t)(M3 / F2_BIG + 1)));
+    LT_TRY(scratch.alloc(&nbig3, 1));
+    {
+        ProfScope prof("gcn3_plan3", s);
+        k_expand<<<(unsigned)ceil_div(E2, 256), 256, 0, s>>>(e2_j, e2_s, E2, b_indptr, b_i, b_w, off3, key3, val3);
+        LT_LAUNCH_CHECK();
+        BitRange ranges[2] = {{0, bits_for((uint64_t)(T - 1))}, {32, 32 + bits_for((uint64_t)(Ts > 1 ? Ts - 1 : 1))}};
+        LT_TRY(radix_sort_u64(key3, val3, M3, ranges, Ts > 1 ? 2 : 1, s));
+        LT_TRY(group_records(key3, M3, grp3, ng3, big3, nbig3, scratch, s));
+    }
+    LT_TRY(frontier_reduce(key3, val3, grp3, ng3, big3, nbig3, M3, dq2, c, c, out, ldo, s));
+    if (info) {
+        int32_t g = 0;
+        LT_CUDA(cudaMemcpyAsync(&g, ng3, 4, cudaMemcpyDeviceToHost, s));
+        LT_CUDA(cudaStreamSynchronize(s));
+        info->pairs += g;
+    }
+    return LT_OK;
+}
+
+int attack_efficient3(const int32_t* indptr, const int32_t* indices, const float* values, int32_t n, const float* X,
+                      int64_t ldx, int32_t f, const float* W1, const float* b1, const float* W2, const float* b2,
+                      const float* W3, int32_t h1, int32_t h2, int32_t c, const int32_t* test_nodes, int32_t T, int32_t lo,
+                      int32_t hi, float delta, float* out, int64_t ldo, int64_t max_chunk_records, int64_t* info_host,
+                      cudaStream_t s) {
+    const int32_t Ts = hi - lo;
+    Scratch scratch(s);
+    // ---- dense precompute for every node: P = X·W1, H1 = Â·P + b1, H2 = Â·(relu(H1)·W2) + b2   (layers.py:31-34 twice)
+    const int64_t ld1 = h1, ld2 = (h2 + 3) / 4 * 4;
+    float *P, *H1, *R1, *G, *H2;
+    LT_TRY(scratch.alloc(&P, (size_t)n * ld1));
+    LT_TRY(scratch.alloc(&H1, (size_t)n * ld1));
+    LT_TRY(scratch.alloc(&R1, (size_t)n * ld1));
+    LT_TRY(scratch.alloc(&G, (size_t)n * ld2));
+    LT_TRY(scratch.alloc(&H2, (size_t)n * ld2));
+    {
+        ProfScope prof("gcn3_precompute", s);
+        LT_TRY(gemm_f32(X, ldx, nullptr, W1, h1, 0, nullptr, 0, P, ld1, n, h1, f, 0, s));
+        LT_TRY(spmm_csr_f32(indptr, indices, values, n, nullptr, n, P, ld1, h1, b1, 0, H1, ld1, s));
+        const int64_t count4 = (int64_t)n * ld1 / 4;
+        k3_relu_copy<<<(unsigned)ceil_div(count4, 256), 256, 0, s>>>(reinterpret_cast<const float4*>(H1), reinterpret_cast<float4*>(R1), count4);
+        LT_LAUNCH_CHECK();
+        if (ld2 != h2) LT_CUDA(cudaMemsetAsync(G, 0, (size_t)n * ld2 * 4, s));
+        LT_TRY(gemm_f32(R1, ld1, nullptr, W2, h2, 0, nullptr, 0, G, ld2, n, h2, h1, 0, s));
+        LT_TRY(spmm_csr_f32(indptr, indices, values, n, nullptr, n, G, ld2, h2, b2, 0, H2, ld2, s));
+    }
+
+    // ---- observer lists over all n nodes: s → (i, Â[u_i,s]) for every test node u_i adjacent to s
+    int32_t *all_len, *b_indptr, *cursor, *b_i;
+    float* b_w;
+    int64_t* cost;
+    LT_TRY(scratch.alloc(&all_len, (size_t)T + 1));
+    LT_TRY(scratch.alloc(&b_indptr, (size_t)n + 1));
+    LT_TRY(scratch.alloc(&cursor, (size_t)n + 1));
+    LT_TRY(scratch.alloc(&cost, (size_t)Ts));
+    k_test_lens<<<(unsigned)ceil_div(T, 256), 256, 0, s>>>(indptr, test_nodes, T, n, 0, 0, all_len, nullptr);
+    LT_LAUNCH_CHECK();
+    LT_TRY(exclusive_scan_i32(all_len, all_len, T, s));
+    k3_costs<<<(unsigned)ceil_div((int64_t)Ts * 32, 256), 256, 0, s>>>(indptr, indices, test_nodes, lo, Ts, n, cost);
+    LT_LAUNCH_CHECK();
+    int32_t nb_cap = 0;
+    int64_t* cost_h = (int64_t*)malloc((size_t)Ts * 8);
+    if (!cost_h) { set_error("lt_attack_efficient3: host allocation failed"); return LT_ERR_NOMEM; }
+    struct HostGuard { void* p; ~HostGuard() { free(p); } } hguard{cost_h};
+    LT_CUDA(cudaMemcpyAsync(&nb_cap, all_len + T, 4, cudaMemcpyDeviceToHost, s));
+    LT_CUDA(cudaMemcpyAsync(cost_h, cost, (size_t)Ts * 8, cudaMemcpyDeviceToHost, s));
+    LT_CUDA(cudaStreamSynchronize(s));
+    LT_TRY(scratch.alloc(&b_i, (size_t)nb_cap));
+    LT_TRY(scratch.alloc(&b_w, (size_t)nb_cap));
+    LT_CUDA(cudaMemsetAsync(b_indptr, 0, ((size_t)n + 1) * 4, s));
+    const unsigned blT = (unsigned)ceil_div(nb_cap > 0 ? nb_cap : 1, 256);
+    k_observers<0><<<blT, 256, 0, s>>>(indptr, indices, values, test_nodes, T, all_len, nullptr, b_indptr, nullptr, nullptr);
+    LT_LAUNCH_CHECK();
+    LT_TRY(exclusive_scan_i32(b_indptr, b_indptr, n, s));
+    LT_CUDA(cudaMemcpyAsync(cursor, b_indptr, ((size_t)n + 1) * 4, cudaMemcpyDeviceToDevice, s));
+    k_observers<1><<<blT, 256, 0, s>>>(indptr, indices, values, test_nodes, T, all_len, nullptr, cursor, b_i, b_w);
+    LT_LAUNCH_CHECK();
+
+    // ---- chunks of perturbed nodes: stage-2 records per chunk bounded by the memory budget
+    int64_t cap = max_chunk_records;
+    if (cap <= 0) {
+        size_t free_b = 0, total_b = 0;
+        LT_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        const int64_t per_rec = 48 + 4 * (int64_t)ld2 + 4 * (int64_t)c + 192;   // records ×2 (sort), ΔR2/ΔQ2 rows, stage-3 records
+        cap = (int64_t)(free_b / 3) / per_rec;
+        if (cap > ((int64_t)1 << 30)) cap = (int64_t)1 << 30;
+        if (cap < 1) cap = 1;
+    }
+    Gcn3Info info;
+    int32_t a = 0;
+    while (a < Ts) {
+        int32_t b = a;
+        int64_t acc = 0;
+        while (b < Ts && (b == a || acc + cost_h[b] <= cap)) acc += cost_h[b++];
+        LT_TRY(gcn3_chunk(indptr, indices, values, n, test_nodes, T, lo + a, lo + b, P, H1, ld1, H2, ld2, W2, W3, h1, h2, c,
+                          b_indptr, b_i, b_w, delta, out + (int64_t)a * ldo, ldo, &info, s));
+        a = b;
+    }
+    if (info_host) {
+        info_host[0] = info.chunks; info_host[1] = info.E1; info_host[2] = info.M2; info_host[3] = info.E2;
+        info_host[4] = info.M3; info_host[5] = info.pairs; info_host[6] = 0; info_host[7] = 0;
+    }
+    return LT_OK;
 }
 
 }  // namespace lt
@@ -756,4 +1103,20 @@ extern "C" int lt_attack_efficient(const int32_t* indptr, const int32_t* indices
     }
     lt_plan_destroy(plan, stream);
     return st;
+}
+
+// --n-layer 3: the same call for GCN3 (gcn/models.py:28-46)
+extern "C" int lt_attack_efficient3(const int32_t* indptr, const int32_t* indices, const float* values, int32_t n,
+                                    const float* X, int64_t ldx, int32_t f, const float* W1, const float* b1,
+                                    const float* W2, const float* b2, const float* W3, int32_t h1, int32_t h2, int32_t c,
+                                    const int32_t* test_nodes, int32_t T, int32_t lo, int32_t hi, float delta, float* out,
+                                    int64_t ldo, int64_t max_chunk_records, int64_t* info_host, lt_stream_t stream) {
+    LT_CHECK_ARG(indptr && indices && values && X && W1 && b1 && W2 && b2 && W3 && test_nodes && out,
+                 "lt_attack_efficient3: null pointer");
+    LT_CHECK_ARG(n > 0 && f > 0 && h1 > 0 && h2 > 0 && c > 0 && ldx >= f && h1 % 4 == 0 && T > 0 && lo >= 0 && hi >= lo &&
+                     hi <= T && ldo >= T && delta != 0.f,
+                 "lt_attack_efficient3: sizes (h1 % 4 == 0, 0 <= lo <= hi <= T <= ldo)");
+    if (hi == lo) return LT_OK;
+    return attack_efficient3(indptr, indices, values, n, X, ldx, f, W1, b1, W2, b2, W3, h1, h2, c, test_nodes, T, lo, hi,
+                             delta, out, ldo, max_chunk_records, info_host, (cudaStream_t)stream);
 }

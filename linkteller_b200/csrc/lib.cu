@@ -135,3 +135,28 @@ extern "C" int lt_gcn_forward(const int32_t* indptr, const int32_t* indices, con
     LT_TRY(spmm_csr_f32(indptr, indices, values, n, nullptr, n, Q, c, c, b2, 0, logits, ldz, s));
     return LT_OK;
 }
+
+// GCN3.forward (gcn/models.py:40-46), eval mode: Z = Â·(relu(Â·(relu(Â·(X·W1) + b1)·W2) + b2)·W3) + b3
+extern "C" int lt_gcn3_forward(const int32_t* indptr, const int32_t* indices, const float* values, int32_t n,
+                               const float* X, int64_t ldx, int32_t f, const float* W1, const float* b1,
+                               const float* W2, const float* b2, const float* W3, const float* b3, int32_t h1,
+                               int32_t h2, int32_t c, float* logits, int64_t ldz, lt_stream_t stream) {
+    LT_CHECK_ARG(indptr && indices && values && X && W1 && W2 && W3 && logits, "lt_gcn3_forward: null pointer");
+    LT_CHECK_ARG(n > 0 && f > 0 && h1 > 0 && h2 > 0 && c > 0 && ldx >= f && ldz >= c, "lt_gcn3_forward: sizes");
+    cudaStream_t s = (cudaStream_t)stream;
+    Scratch scratch(s);
+    float *P, *R1, *G, *R2, *Q;
+    const int64_t p1 = (h1 + 3) / 4 * 4, p2 = (h2 + 3) / 4 * 4;   // padded leading dimensions keep the float4 SpMM path
+    LT_TRY(scratch.alloc(&P, (size_t)n * p1));
+    LT_TRY(scratch.alloc(&R1, (size_t)n * p1));
+    LT_TRY(scratch.alloc(&G, (size_t)n * p2));
+    LT_TRY(scratch.alloc(&R2, (size_t)n * p2));
+    LT_TRY(scratch.alloc(&Q, (size_t)n * c));
+    LT_TRY(gemm_f32(X, ldx, nullptr, W1, h1, 0, nullptr, 0, P, p1, n, h1, f, 0, s));
+    LT_TRY(spmm_csr_f32(indptr, indices, values, n, nullptr, n, P, p1, h1, b1, 1, R1, p1, s));
+    LT_TRY(gemm_f32(R1, p1, nullptr, W2, h2, 0, nullptr, 0, G, p2, n, h2, h1, 0, s));
+    LT_TRY(spmm_csr_f32(indptr, indices, values, n, nullptr, n, G, p2, h2, b2, 1, R2, p2, s));
+    LT_TRY(gemm_f32(R2, p2, nullptr, W3, c, 0, nullptr, 0, Q, c, n, c, h2, 0, s));
+    LT_TRY(spmm_csr_f32(indptr, indices, values, n, nullptr, n, Q, c, c, b3, 0, logits, ldz, s));
+    return LT_OK;
+}

@@ -1,4 +1,4 @@
-"""GraphConvolution / GCN with the reference's module API (gcn/layers.py:8-41, gcn/models.py:8-25):
+"""GraphConvolution / GCN / GCN3 with the reference's module API (gcn/layers.py:8-41, gcn/models.py:8-46):
 same constructors, parameter names, [in,out] weight layout, U(±1/√out) init and state-dict keys
 (gc1.weight, gc1.bias, gc2.weight, gc2.bias), so checkpoints written by either load in the other.
 
@@ -121,3 +121,25 @@ class GCN(nn.Module):
         x = F.relu(self.gc1(x, adj))
         x = F.dropout(x, self.dropout, training=self.training)
         return self.gc2(x, adj)
+
+
+class GCN3(nn.Module):
+    """gc1 → ReLU → dropout → gc2 → ReLU → dropout → gc3, raw logits (gcn/models.py:28-46; --n-layer 3)."""
+
+    def __init__(self, nfeat, nhid1, nhid2, nclass, dropout):
+        super().__init__()
+        self.gc1 = GraphConvolution(nfeat, nhid1)
+        self.gc2 = GraphConvolution(nhid1, nhid2)
+        self.gc3 = GraphConvolution(nhid2, nclass)
+        self.dropout = dropout
+
+    def forward(self, x, adj):
+        if not self.training and not torch.is_grad_enabled():
+            return ops.gcn3_forward(_csr_pair(adj)[0], x.to(torch.float32), self.gc1.weight.detach(),
+                                    self.gc1.bias.detach(), self.gc2.weight.detach(), self.gc2.bias.detach(),
+                                    self.gc3.weight.detach(), self.gc3.bias.detach())
+        x = F.relu(self.gc1(x, adj))
+        x = F.dropout(x, self.dropout, training=self.training)
+        x = F.relu(self.gc2(x, adj))
+        x = F.dropout(x, self.dropout, training=self.training)
+        return self.gc3(x, adj)

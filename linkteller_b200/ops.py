@@ -243,6 +243,33 @@ def gcn_forward(adj: DeviceCSR, x, w1, b1, w2, b2) -> torch.Tensor:
     return out
 
 
+def gcn3_forward(adj: DeviceCSR, x, w1, b1, w2, b2, w3, b3) -> torch.Tensor:
+    """GCN3.forward in eval mode (gcn/models.py:40-46): raw logits [n,c] in one C call."""
+    lib = _lib.load()
+    x, ldx = _rowmajor(x, "x")
+    w1 = _chk(w1, torch.float32, "w1", 2)
+    w2 = _chk(w2, torch.float32, "w2", 2)
+    w3 = _chk(w3, torch.float32, "w3", 2)
+    n, f = x.shape
+    h1, h2 = w2.shape
+    c = w3.shape[1]
+    if w1.shape != (f, h1) or w3.shape[0] != h2:
+        raise ValueError(f"GCN3 weight shapes do not chain: {tuple(w1.shape)}, {tuple(w2.shape)}, {tuple(w3.shape)}")
+    out = torch.empty((n, c), dtype=torch.float32, device=x.device)
+    _lib.check(lib.lt_gcn3_forward(_p(adj.indptr), _p(adj.indices), _p(adj.values), n, _p(x), ldx, f, _p(w1), _p(b1),
+                                   _p(w2), _p(b2), _p(w3), _p(b3), h1, h2, c, _p(out), c, _stream()), "lt_gcn3_forward")
+    return out
+
+
+def model_forward(adj: DeviceCSR, x, weights) -> torch.Tensor:
+    """Raw logits of the model the weights belong to: 4 tensors → GCN, 6 → GCN3 (gcn_trainer.py:81-90)."""
+    if len(weights) == 4:
+        return gcn_forward(adj, x, *weights)
+    if len(weights) == 6:
+        return gcn3_forward(adj, x, *weights)
+    raise NotImplementedError(f'n_layer = {len(weights) // 2} not implemented!')
+
+
 # ------------------------------------------------------------------------------------------ a7/a8
 INFO_KEYS = ("frontier_rows", "incidences", "observer_entries", "records", "support_pairs", "frontier_bytes",
              "frontier_row_nnz", "reserved")
@@ -275,6 +302,69 @@ def attack_efficient(adj: DeviceCSR, x, w1, b1, w2, test_nodes: torch.Tensor, de
     if want_info:
         return out, dict(zip(INFO_KEYS, list(info)))
     return out
+
+
+INFO3_KEYS = ("chunks", "hop1_incidences", "hop2_records", "hop2_incidences", "hop3_records", "support_pairs",
+              "reserved0", "reserved1")
+
+
+def _pad_first_hidden(w1, b1, w2):
+    """The frontier kernels read H1 / P rows as float4: pad the first hidden width to a multiple of 4 with
+    zero units (zero column of W1, zero bias, zero row of W2 — such a unit never fires and feeds nothing)."""
+    h = w1.shape[1]
+    pad = (-h) % 4
+    if pad == 0:
+        return w1, b1, w2
+    return (torch.nn.functional.pad(w1, (0, pad)).contiguous(), torch.nn.functional.pad(b1, (0, pad)).contiguous(),
+            torch.nn.functional.pad(w2, (0, 0, 0, pad)).contiguous())
+
+
+def attack_efficient3(adj: DeviceCSR, x, w1, b1, w2, b2, w3, test_nodes: torch.Tensor, delta: float,
+                      lo: int = 0, hi: Optional[int] = None, out: Optional[torch.Tensor] = None,
+                      want_info: bool = False, max_chunk_records: int = 0):
+    """Influence rows [hi-lo, T] of the three-layer model (--n-layer 3, GCN3) for the perturbed nodes
+    test_nodes[lo:hi] in one C call (lt_attack_efficient3)."""
+    lib = _lib.load()
+    x, ldx = _rowmajor(x, "x")
+    w1 = _chk(w1, torch.float32, "w1", 2)
+    w2 = _chk(w2, torch.float32, "w2", 2)
+    w3 = _chk(w3, torch.float32, "w3", 2)
+    _chk(b1, torch.float32, "b1", 1)
+    _chk(b2, torch.float32, "b2", 1)
+    _chk(test_nodes, torch.int32, "test_nodes", 1)
+    _chk(adj.values, torch.float32, "adj.values", 1)
+    w1, b1, w2 = _pad_first_hidden(w1, b1, w2)
+    T = test_nodes.numel()
+    hi = T if hi is None else hi
+    n, f = x.shape
+    h1, h2 = w2.shape
+    c = w3.shape[1]
+    if w1.shape != (f, h1) or w3.shape[0] != h2 or b1.numel() != h1 or b2.numel() != h2:
+        raise ValueError(f"GCN3 weight shapes do not chain: {tuple(w1.shape)}, {tuple(w2.shape)}, {tuple(w3.shape)}")
+    if out is None:
+        out = torch.empty((hi - lo, T), dtype=torch.float32, device=x.device)
+    else:
+        _chk(out, torch.float32, "out", 2)
+    info = (C.c_int64 * 8)()
+    _lib.check(lib.lt_attack_efficient3(_p(adj.indptr), _p(adj.indices), _p(adj.values), n, _p(x), ldx, f, _p(w1),
+                                        _p(b1), _p(w2), _p(b2), _p(w3), h1, h2, c, _p(test_nodes), T, lo, hi,
+                                        float(delta), _p(out), out.stride(0), int(max_chunk_records),
+                                        info if want_info else None, _stream()), "lt_attack_efficient3")
+    if want_info:
+        return out, dict(zip(INFO3_KEYS, list(info)))
+    return out
+
+
+def attack_rows(adj: DeviceCSR, x, weights, test_nodes: torch.Tensor, delta: float, lo: int = 0,
+                hi: Optional[int] = None, out: Optional[torch.Tensor] = None, want_info: bool = False):
+    """Influence rows for the model the weights belong to — (w1,b1,w2,b2): GCN, (w1,b1,w2,b2,w3,b3): GCN3.
+    The last bias cancels in the finite difference and is not read."""
+    if len(weights) == 4:
+        w1, b1, w2 = _pad_first_hidden(weights[0], weights[1], weights[2])
+        return attack_efficient(adj, x, w1, b1, w2, test_nodes, delta, lo=lo, hi=hi, out=out, want_info=want_info)
+    if len(weights) == 6:
+        return attack_efficient3(adj, x, *weights[:5], test_nodes, delta, lo=lo, hi=hi, out=out, want_info=want_info)
+    raise NotImplementedError(f'n_layer = {len(weights) // 2} not implemented!')
 
 
 class Plan:
@@ -458,7 +548,7 @@ def pair_gather(mat: torch.Tensor, rows: torch.Tensor, cols: torch.Tensor, row0:
 
 
 def pair_influence(adj: DeviceCSR, x, w1, b1, w2, perturbed: torch.Tensor, observed: torch.Tensor, delta: float,
-                   block_bytes: int = 512 << 20) -> torch.Tensor:
+                   block_bytes: int = 512 << 20, b2=None, w3=None) -> torch.Tensor:
     """‖((f(X + δ·e_p x_pᵀ) − f(X))/δ)[o]‖₂ for LISTED (perturbed p, observed o) node pairs — what
     link_prediction_attack_efficient_balanced (attacker.py:250-284) and the naive attack
     (attacker.py:143-160) read one entry at a time.  Every node is a candidate observer, so influence
@@ -486,7 +576,10 @@ def pair_influence(adj: DeviceCSR, x, w1, b1, w2, perturbed: torch.Tensor, obser
         hi = min(n, lo + rows_per_block)
         if not need[lo:hi].any():
             continue
-        attack_efficient(adj, x, w1, b1, w2, all_nodes, delta, lo=lo, hi=hi, out=buf[: hi - lo])
+        if w3 is None:
+            attack_efficient(adj, x, w1, b1, w2, all_nodes, delta, lo=lo, hi=hi, out=buf[: hi - lo])
+        else:                                        # three-layer model: b2 and W3 given
+            attack_efficient3(adj, x, w1, b1, w2, b2, w3, all_nodes, delta, lo=lo, hi=hi, out=buf[: hi - lo])
         _lib.check(lib.lt_pair_gather(_p(buf), buf.stride(0), lo, hi - lo, _p(perturbed), _p(observed), K, _p(out),
                                       _stream()), "lt_pair_gather")
     return out[:K]

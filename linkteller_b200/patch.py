@@ -7,6 +7,7 @@ those names to the B200 implementations, leaving every reference file untouched:
     attacker.Attacker, gcn_trainer.Attacker          → linkteller_b200.attacker.Attacker
     gcn.layers.GraphConvolution.forward              → sm_100a gemm + CSR SpMM (autograd kept)
     gcn.models.GCN.forward (eval, no_grad)           → lt_gcn_forward
+    gcn.models.GCN3.forward (eval, no_grad)          → lt_gcn3_forward   (--n-layer 3)
     utils.fetch_normalization, worker.fetch_normalization            → device Â build (bit-exact)
     worker.Worker.perturb_adj                        → host RNG + device apply (EdgeRand / Lapgraph)
 
@@ -87,8 +88,20 @@ def install(reference_path=None, patch_layers=True, patch_normalization=True, pa
                                        self.gc1.bias.detach(), self.gc2.weight.detach(), self.gc2.bias.detach())
             return ref_gcn_forward(self, x, adj)
 
+        ref_gcn3_forward = getattr(getattr(models, "GCN3", None), "forward", None)
+
+        def gcn3_forward(self, x, adj):
+            if not self.training and not torch.is_grad_enabled() and x.is_cuda:
+                return ops.gcn3_forward(_gcn._csr_pair(adj)[0], x.to(torch.float32), self.gc1.weight.detach(),
+                                        self.gc1.bias.detach(), self.gc2.weight.detach(), self.gc2.bias.detach(),
+                                        self.gc3.weight.detach(), self.gc3.bias.detach())
+            return ref_gcn3_forward(self, x, adj)
+
         layers.GraphConvolution.forward = gc_forward
         models.GCN.forward = gcn_forward
+        if ref_gcn3_forward is not None:
+            models.GCN3.forward = gcn3_forward
+            done[("gcn.models", "GCN3.forward")] = gcn3_forward
         done[("gcn.layers", "GraphConvolution.forward")] = gc_forward
         done[("gcn.models", "GCN.forward")] = gcn_forward
 

@@ -196,6 +196,11 @@ REF_STUBS = {
                       "class GCN(torch.nn.Module):\n"
                       "    def __init__(self, f, h, c, dropout):\n        super().__init__()\n"
                       "        self.gc1 = GraphConvolution(f, h); self.gc2 = GraphConvolution(h, c); self.dropout = dropout\n"
+                      "    def forward(self, x, adj):\n        raise RuntimeError('reference path')\n"
+                      "class GCN3(torch.nn.Module):\n"
+                      "    def __init__(self, f, h1, h2, c, dropout):\n        super().__init__()\n"
+                      "        self.gc1 = GraphConvolution(f, h1); self.gc2 = GraphConvolution(h1, h2)\n"
+                      "        self.gc3 = GraphConvolution(h2, c); self.dropout = dropout\n"
                       "    def forward(self, x, adj):\n        raise RuntimeError('reference path')\n"),
     "utils/__init__.py": "from .load import *\n",
     "utils/load.py": "def fetch_normalization(type):\n    return lambda adj: 'reference path'\n",
@@ -228,6 +233,17 @@ def test_patch_install_rebinds_reference_names(golden, tmp_path, monkeypatch):
     with torch.no_grad():
         z = model(wk.features, wk.adj_full)                     # would raise 'reference path' if not rebound
     assert np.abs(z.cpu().numpy() - g["a5_logits"]).max() <= 1e-4 * max(1.0, np.abs(g["a5_logits"]).max())
+    from gcn.models import GCN3                                 # --n-layer 3 (gcn_trainer.py:81-86)
+    w3 = synth.gcn3_weights(s.f, 16, 8, s.c, seed=1)
+    m3 = GCN3(s.f, 16, 8, s.c, 0.5)
+    m3.load_state_dict({k: torch.from_numpy(a) for k, a in zip(
+        ("gc1.weight", "gc1.bias", "gc2.weight", "gc2.bias", "gc3.weight", "gc3.bias"), w3)})
+    m3 = m3.cuda().eval()
+    with torch.no_grad():
+        z3 = m3(wk.features, wk.adj_full)
+    coo0 = (g["a2_row"], g["a2_col"], g["a2_val"])
+    ref3 = O.gcn_forward_np(s.features, coo0, w3, s.n, torch.float64)
+    assert np.abs(z3.cpu().numpy() - ref3).max() <= 1e-4 * max(1.0, np.abs(ref3).max())
     ori = sp.csr_matrix((g["a1_data"], g["a1_indices"], g["a1_indptr"]), shape=(s.n, s.n))
     coo = worker.fetch_normalization("FirstOrderGCN")(ori)
     assert np.array_equal(coo.row, g["a2_row"]) and np.array_equal(coo.data.astype(np.float32), g["a2_val"])
