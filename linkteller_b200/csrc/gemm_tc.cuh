@@ -124,7 +124,8 @@ k_gemm_tc(Prod prod, const uint32_t* __restrict__ Bimg, const float* __restrict_
     __shared__ uint32_t tmem_base_s;
     __shared__ int64_t meta0[2][TC_BM], meta1[2][TC_BM];
     __shared__ float meta2[2][TC_BM];
-    __shared__ __align__(16) float bias_s[NT];               // this CTA's slice of the bias row (zeros without bias)
+    constexpr int NT32 = (NT + 31) / 32 * 32;                // the epilogue walks 32-column groups
+    __shared__ __align__(16) float bias_s[NT32];             // this CTA's slice of the bias row (zeros without bias)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
@@ -137,7 +138,7 @@ k_gemm_tc(Prod prod, const uint32_t* __restrict__ Bimg, const float* __restrict_
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     const int n0 = blockIdx.y * NT;                          // first column of this CTA's N tile
-    for (int j = tid; j < NT; j += TC_THREADS) bias_s[j] = (bias && n0 + j < N) ? __ldg(bias + n0 + j) : 0.f;
+    for (int j = tid; j < NT32; j += TC_THREADS) bias_s[j] = (bias && j < NT && n0 + j < N) ? __ldg(bias + n0 + j) : 0.f;
     const int tiles_m = (M + TC_BM - 1) / TC_BM;
     const int my_tiles = blockIdx.x < tiles_m ? (tiles_m - 1 - blockIdx.x) / gridDim.x + 1 : 0;
 
@@ -237,38 +238,50 @@ k_gemm_tc(Prod prod, const uint32_t* __restrict__ Bimg, const float* __restrict_
             constexpr int HALVES = NT >= 64 ? 2 : 1;
             constexpr int COLS_PER_HALF = NT / HALVES;
             const int q = warp & 3, half = warp >> 2;
-            const int m = (blockIdx.x + tile_idx * gridDim.x) * TC_BM + q * 32 + lane;
+            const int m_base = (blockIdx.x + tile_idx * gridDim.x) * TC_BM + q * 32;
             const bool vec4 = (ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+            // A lane holds 32 columns of ONE row after the TMEM load; stored as is, a warp-wide store would touch 32
+            // different 128-byte lines (ncu r1g: the epilogue was half of the kernel, one L1 tag per lane per store).
+            // The 32x32 block is transposed through this warp's 4 KB of the stage-s A buffer (free: every MMA of the
+            // tile has completed; 16-byte chunks XOR-swizzled by the row, conflict-free both ways) so that eight
+            // lanes write one row's 128 contiguous bytes and a store instruction covers four full lines.
+            uint8_t* xp = st + warp * 4096;
             if (half < HALVES) {
 #pragma unroll 1
                 for (int c0 = half * COLS_PER_HALF; c0 < (half + 1) * COLS_PER_HALF; c0 += 32) {
                     uint32_t v[32];
                     tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-                    if (m < M) {
-                        float* dst = C + (int64_t)m * ldc;
-                        const int lim = min((half + 1) * COLS_PER_HALF - c0, 32);   // valid columns of this load
+                    const int lim = min((half + 1) * COLS_PER_HALF - c0, 32);   // valid columns of this load
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            const int col = n0 + c0 + j;
-                            if (j >= lim || col >= N) continue;
-                            // bias from shared memory (one broadcast float4 per four columns): a global load per
-                            // element here was the kernel's top stall (ncu r1c: FADD waiting on long_scoreboard)
-                            const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c0 + j);
-                            float x[4] = {__uint_as_float(v[j]) + b4.x, __uint_as_float(v[j + 1]) + b4.y,
-                                          __uint_as_float(v[j + 2]) + b4.z, __uint_as_float(v[j + 3]) + b4.w};
-                            if (relu) {
+                    for (int j = 0; j < 32; j += 4) {
+                        // bias from shared memory (one broadcast float4 per four columns)
+                        const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c0 + j);
+                        float4 x = make_float4(__uint_as_float(v[j]) + b4.x, __uint_as_float(v[j + 1]) + b4.y,
+                                               __uint_as_float(v[j + 2]) + b4.z, __uint_as_float(v[j + 3]) + b4.w);
+                        if (relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
+                        *reinterpret_cast<float4*>(xp + lane * 128 + ((((j >> 2) ^ lane) & 7) << 4)) = x;
+                    }
+                    __syncwarp();
+                    const int c4 = lane & 7;
+                    const int col = n0 + c0 + c4 * 4;
 #pragma unroll
-                                for (int u = 0; u < 4; ++u) x[u] = fmaxf(x[u], 0.f);
-                            }
-                            if (vec4 && j + 4 <= lim && col + 4 <= N) {
-                                *reinterpret_cast<float4*>(dst + col) = make_float4(x[0], x[1], x[2], x[3]);
+                    for (int i = 0; i < 8; ++i) {
+                        const int rl = 4 * i + (lane >> 3);
+                        const float4 x = *reinterpret_cast<const float4*>(xp + rl * 128 + (((c4 ^ rl) & 7) << 4));
+                        const int m = m_base + rl;
+                        if (m < M && c4 * 4 < lim && col < N) {
+                            float* dst = C + (int64_t)m * ldc + col;
+                            if (vec4 && c4 * 4 + 4 <= lim && col + 4 <= N) {
+                                *reinterpret_cast<float4*>(dst) = x;
                             } else {
+                                const float xs[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
                                 for (int u = 0; u < 4; ++u)
-                                    if (j + u < lim && col + u < N) dst[col + u] = x[u];
+                                    if (c4 * 4 + u < lim && col + u < N) dst[u] = xs[u];
                             }
                         }
                     }
+                    __syncwarp();
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
