@@ -131,7 +131,8 @@ int lt_plan_create(const int32_t* indptr, const int32_t* indices, const float* v
                    lt_plan** plan_host);
 int lt_plan_destroy(lt_plan* plan, lt_stream_t stream);
 /* info_host[0..7]: |R|, incidences E, observer entries, records, pairs in the support,
- * algorithmic bytes of one lt_influence_rows (for h,c below), Σ_{r∈R} nnz(Â[r,:]), reserved */
+ * algorithmic bytes of one lt_influence_rows (for h,c below), Σ_{r∈R} nnz(Â[r,:]),
+ * incidences whose ReLUs could switch and took the exact recomputed path (lt_attack_efficient only, else 0) */
 int lt_plan_info(const lt_plan* plan, int32_t h, int32_t c, int64_t* info_host, lt_stream_t stream);
 const int32_t* lt_plan_rows(const lt_plan* plan);
 /* copies the |R| frontier row ids (ascending node ids) into dst (capacity info[0]) */

@@ -405,14 +405,115 @@ struct DeltaRProd {
         o1 = (int64_t)(p_index ? p_index[j] : j) * ldp;
         f = s_a[e];
     }
-    __device__ __forceinline__ TcRaw raw(int64_t o0, int64_t o1, int k) const { return TcRaw{__ldg(H + o0 + k), __ldg(P + o1 + k)}; }
-    __device__ __forceinline__ float value(TcRaw r, float a) const {
-        const float hh = r.x, p = r.y;
+    // h, ldh, ldp are multiples of 4 and H, P 16-byte aligned (checked by frontier_dq): always one 16-byte load each
+    __device__ __forceinline__ TcRaw4 raw4(int64_t o0, int64_t o1, int k, int) const {
+        return TcRaw4{__ldg(reinterpret_cast<const float4*>(H + o0 + k)), __ldg(reinterpret_cast<const float4*>(P + o1 + k))};
+    }
+    __device__ __forceinline__ float value(float hh, float p, float a) const {
         const float hp = fmaf(delta * a, p, hh);           // H'[r,k]
         if (hh > 0.f) return hp > 0.f ? a * p : -hh * inv_delta;
         return hp > 0.f ? hp * inv_delta : 0.f;
     }
 };
+
+// A operand of F1 when only the SIGNS of H are kept (sign-mask path of lt_attack_efficient): where no ReLU of the
+// row can change sign — the row's smallest |H| exceeds |δ·a|·max|P[v]| — ΔR[e,k] is a·P[v,k] on the active units
+// and 0 elsewhere, exactly the values DeltaRProd computes from the H row, but read from 32 bytes instead of 1 KB.
+// Rows that fail the test are corrected afterwards by k_flip_fix.
+struct MaskProd {
+    const int32_t* s_j; const int32_t* s_rho; const float* s_a; const int32_t* p_index;
+    const uint32_t* sign_words; int32_t wpr; const float* P; int64_t ldp;
+    __device__ __forceinline__ void meta(int e, int64_t& o0, int64_t& o1, float& f) const {
+        const int32_t j = s_j[e];
+        o0 = (int64_t)s_rho[e] * wpr;
+        o1 = (int64_t)(p_index ? p_index[j] : j) * ldp;
+        f = s_a[e];
+    }
+    __device__ __forceinline__ TcRaw4 raw4(int64_t o0, int64_t o1, int k, int) const {
+        const uint32_t w = __ldg(sign_words + o0 + (k >> 5)) >> (k & 31);
+        return TcRaw4{__ldg(reinterpret_cast<const float4*>(P + o1 + k)),
+                      make_float4(__uint_as_float(w & 1u), __uint_as_float((w >> 1) & 1u), __uint_as_float((w >> 2) & 1u),
+                                  __uint_as_float((w >> 3) & 1u))};
+    }
+    __device__ __forceinline__ float value(float p, float bit, float a) const { return __float_as_uint(bit) ? a * p : 0.f; }
+};
+
+// pmax[j] = max_k |P[j,k]|; one warp per row
+__global__ void k_row_absmax(const float* __restrict__ P, int64_t ldp, int32_t rows, int32_t h, float* __restrict__ pmax) {
+    const int lane = threadIdx.x & 31;
+    const int64_t j = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (j >= rows) return;
+    float m = 0.f;
+    for (int k = lane; k < h; k += 32) m = fmaxf(m, fabsf(P[j * ldp + k]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(LT_FULL, m, o));
+    if (lane == 0) pmax[j] = m;
+}
+
+// One warp per incidence.  Rows whose smallest |H| cannot be crossed by the perturbation return at once (the
+// masked product is exact for them).  For the others H[r,:] = AX[r,:]·W1 + b1 is recomputed in fp32 (a lane owns
+// the hidden units lane, lane+32, …: up to eight independent accumulators, W1 rows read coalesced), ΔR is
+// evaluated case by case as in DeltaRProd, and the difference to the masked value — non-zero only where a ReLU
+// switches — is pushed through W2 into ΔQ[e,:].
+__global__ void __launch_bounds__(256)
+k_flip_fix(const int32_t* __restrict__ s_j, const int32_t* __restrict__ s_rho, const float* __restrict__ s_a, int64_t E,
+           const float* __restrict__ AX, int64_t ldax, int32_t f, const float* __restrict__ W1, const float* __restrict__ b1,
+           const float* __restrict__ P, int64_t ldp, const int32_t* __restrict__ p_index, const float* __restrict__ pmax,
+           const uint32_t* __restrict__ sign_words, int32_t wpr, const uint32_t* __restrict__ minabs_bits,
+           const float* __restrict__ W2, int32_t h, int32_t c, float delta, float inv_delta, float* __restrict__ dq,
+           int32_t lddq, int32_t* __restrict__ n_fixed) {
+    const int lane = threadIdx.x & 31;
+    const int64_t e = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (e >= E) return;
+    const int32_t j = s_j[e], rho = s_rho[e];
+    const float a = s_a[e];
+    const float thr = fabsf(delta * a) * pmax[j] * 1.001f;
+    if (__uint_as_float(minabs_bits[rho]) > thr) return;
+    if (lane == 0 && n_fixed) atomicAdd(n_fixed, 1);
+    const float* ax = AX + (int64_t)rho * ldax;
+    const float* prow = P + (int64_t)(p_index ? p_index[j] : j) * ldp;
+    const float da = delta * a;
+    for (int k0 = 0; k0 < h; k0 += 256) {
+        float hh[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) { const int k = k0 + lane + 32 * t; hh[t] = k < h ? b1[k] : 0.f; }
+        for (int i0 = 0; i0 < f; i0 += 32) {
+            const float av = i0 + lane < f ? ax[i0 + lane] : 0.f;          // 32 entries of the AX row, one per lane
+            const int cnt = min(32, f - i0);
+            for (int u = 0; u < cnt; ++u) {
+                const float ai = __shfl_sync(LT_FULL, av, u);
+                const float* w1 = W1 + (int64_t)(i0 + u) * h + k0 + lane;
+#pragma unroll
+                for (int t = 0; t < 8; ++t)
+                    if (k0 + lane + 32 * t < h) hh[t] = fmaf(ai, __ldg(w1 + 32 * t), hh[t]);
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+            const int kb = k0 + 32 * t;                                    // warp-uniform
+            if (kb >= h) break;
+            const int k = kb + lane;
+            float d = 0.f;
+            if (k < h) {
+                const float p = prow[k];
+                const float hp = fmaf(da, p, hh[t]);
+                float exact;
+                if (hh[t] > 0.f) exact = hp > 0.f ? a * p : -hh[t] * inv_delta;
+                else exact = hp > 0.f ? hp * inv_delta : 0.f;
+                const uint32_t bit = (sign_words[(int64_t)rho * wpr + (k >> 5)] >> (k & 31)) & 1u;
+                d = exact - (bit ? a * p : 0.f);
+            }
+            uint32_t m = __ballot_sync(LT_FULL, d != 0.f);
+            while (m) {
+                const int src = __ffs(m) - 1;
+                m &= m - 1;
+                const float dk = __shfl_sync(LT_FULL, d, src);
+                const float* w2 = W2 + (int64_t)(kb + src) * c;
+                for (int col = lane; col < c; col += 32) dq[e * lddq + col] = fmaf(dk, w2[col], dq[e * lddq + col]);
+            }
+        }
+    }
+}
 
 static int plan_own(lt_plan* p, void* ptr) {
     if (p->n_owned >= 24) { set_error("plan: too many buffers"); return LT_ERR_INTERNAL; }
@@ -613,6 +714,40 @@ static int frontier_dq(const lt_plan* p, const int32_t* h_index, const float* H,
 #undef LT_F1
         LT_LAUNCH_CHECK();
     }
+    return LT_OK;
+}
+
+// F1 from the sign mask of H_R (see MaskProd): ΔQ = (mask ⊙ a·P[v])·W2 on the tensor cores, then k_flip_fix
+static int frontier_dq_signs(const lt_plan* p, const uint32_t* sign_words, int32_t wpr, const uint32_t* minabs_bits,
+                             const float* AX, int64_t ldax, int32_t f, const float* W1, const float* b1, const float* P,
+                             int64_t ldp, const int32_t* p_index, const float* W2, int32_t h, int32_t c, float delta,
+                             float* dq, int32_t* n_fixed, cudaStream_t s) {
+    const int64_t E = p->E;
+    if (E == 0) return LT_OK;
+    Scratch scratch(s);
+    const int32_t lddq = frontier_lddq(E, h, c);
+    float* pmax;
+    LT_TRY(scratch.alloc(&pmax, (size_t)p->Ts));
+    ProfScope prof("frontier_dq", s);
+    k_row_absmax<<<(unsigned)ceil_div((int64_t)p->Ts * 32, 256), 256, 0, s>>>(P, ldp, p->Ts, h, pmax);
+    LT_LAUNCH_CHECK();
+    const int nt = tc_pick_nt(c);
+    const int32_t n_pad = nt, kchunks = (h + TC_BK - 1) / TC_BK;
+    uint32_t* img;
+    LT_TRY(scratch.alloc(&img, (size_t)kchunks * 2 * n_pad * TC_BK));
+    LT_TRY(tc_prepack_b(W2, c, 0, c, h, n_pad, img, s));
+    const MaskProd prod{p->s_j, p->s_rho, p->s_a, p_index, sign_words, wpr, P, ldp};
+    switch (nt) {
+        case 32: LT_TRY((launch_tc<32, 2>(prod, img, nullptr, 0, dq, lddq, (int32_t)E, c, h, n_pad, kchunks, s))); break;
+        case 48: LT_TRY((launch_tc<48, 2>(prod, img, nullptr, 0, dq, lddq, (int32_t)E, c, h, n_pad, kchunks, s))); break;
+        case 64: LT_TRY((launch_tc<64, 2>(prod, img, nullptr, 0, dq, lddq, (int32_t)E, c, h, n_pad, kchunks, s))); break;
+        case 128: LT_TRY((launch_tc<128, 1>(prod, img, nullptr, 0, dq, lddq, (int32_t)E, c, h, n_pad, kchunks, s))); break;
+        default: LT_TRY((launch_tc<256, 1>(prod, img, nullptr, 0, dq, lddq, (int32_t)E, c, h, n_pad, kchunks, s))); break;
+    }
+    k_flip_fix<<<(unsigned)ceil_div(E * 32, 256), 256, 0, s>>>(p->s_j, p->s_rho, p->s_a, E, AX, ldax, f, W1, b1, P, ldp, p_index,
+                                                               pmax, sign_words, wpr, minabs_bits, W2, h, c, delta, 1.0f / delta, dq,
+                                                               lddq, n_fixed);
+    LT_LAUNCH_CHECK();
     return LT_OK;
 }
 
@@ -1063,15 +1198,62 @@ extern "C" int lt_attack_efficient(const int32_t* indptr, const int32_t* indices
         Scratch scratch(s);
         const int32_t R = plan->R, Ts = plan->Ts;
         float *HR = nullptr, *Pt = nullptr;
-        st = scratch.alloc(&HR, (size_t)R * h);
-        if (st == LT_OK) st = scratch.alloc(&Pt, (size_t)Ts * h);
+        st = scratch.alloc(&Pt, (size_t)Ts * h);
         // P_v = X[v]·W1 for the slice (gathered rows)
         if (st == LT_OK) {
             ProfScope prof("gemm_pv", s);
             st = gemm_f32(X, ldx, test_nodes + lo, W1, h, 0, nullptr, 0, Pt, h, Ts, h, f, 0, s);
         }
         const bool aggregate_first = (f < h) && (f % 4 == 0) && (ldx % 4 == 0) && ((uintptr_t)X % 16 == 0);
-        if (st == LT_OK) {
+        // sign-mask path: H_R is never written — the GEMM keeps one bit per element and the row's smallest magnitude
+        // (36 bytes per frontier row instead of 4h), F1 reads those, and the rows where a ReLU can switch are patched
+        const bool sign_path = aggregate_first && frontier_use_tc(plan->E, h, c) && h >= 16 &&
+                               (int64_t)R * h * f >= ((int64_t)1 << 24) && plan->M > 0 && !getenv("LT_NO_SIGN_PATH");
+        if (st == LT_OK && sign_path) {
+            float* AX = nullptr;
+            uint32_t *signs = nullptr, *minabs = nullptr;
+            float* dq = nullptr;
+            int32_t* n_fixed = nullptr;
+            const int32_t wpr = (h + 31) / 32;
+            const int32_t lddq = frontier_lddq(plan->E, h, c);
+            st = scratch.alloc(&AX, (size_t)R * f);
+            if (st == LT_OK) st = scratch.alloc(&signs, (size_t)R * wpr);
+            if (st == LT_OK) st = scratch.alloc(&minabs, (size_t)R);
+            if (st == LT_OK) st = scratch.alloc(&dq, (size_t)plan->E * lddq);
+            if (st == LT_OK) st = scratch.alloc(&n_fixed, 1);
+            if (st == LT_OK) {
+                ProfScope prof("spmm_ax", s);
+                st = spmm_csr_f32(indptr, indices, values, n, plan->rows, R, X, ldx, f, nullptr, 0, AX, f, s);
+            }
+            if (st == LT_OK) {
+                ProfScope prof("gemm_h", s);
+                if (cudaMemsetAsync(minabs, 0x7f, (size_t)R * 4, s) != cudaSuccess || cudaMemsetAsync(n_fixed, 0, 4, s) != cudaSuccess) {
+                    set_error("lt_attack_efficient: cudaMemsetAsync failed");
+                    st = LT_ERR_CUDA;
+                } else {
+                    st = gemm_3xtf32_signs(AX, f, W1, h, b1, R, h, f, signs, minabs, s);
+                }
+            }
+            if (st == LT_OK && cudaMemset2DAsync(out, (size_t)ldo * 4, 0, (size_t)T * 4, (size_t)Ts, s) != cudaSuccess) {
+                set_error("lt_attack_efficient: cudaMemset2DAsync failed");
+                st = LT_ERR_CUDA;
+            }
+            if (st == LT_OK)
+                st = frontier_dq_signs(plan, signs, wpr, minabs, AX, f, f, W1, b1, Pt, h, nullptr, W2, h, c, delta, dq, n_fixed, s);
+            if (st == LT_OK)
+                st = frontier_reduce(plan->rec_key, plan->rec_val, plan->grp_off, plan->n_groups, plan->big, plan->n_big, plan->M,
+                                     dq, lddq, c, out, ldo, s);
+            if (st == LT_OK && info_host) {
+                st = lt_plan_info(plan, h, c, info_host, stream);
+                int32_t nf = 0;
+                if (st == LT_OK && cudaMemcpyAsync(&nf, n_fixed, 4, cudaMemcpyDeviceToHost, s) == cudaSuccess &&
+                    cudaStreamSynchronize(s) == cudaSuccess)
+                    info_host[7] = nf;      // incidences that took the exact (recomputed) path
+            }
+        } else if (st == LT_OK) {
+            st = scratch.alloc(&HR, (size_t)R * h);
+        }
+        if (st == LT_OK && !sign_path) {
             if (aggregate_first) {
                 // H_R = (Â[R,:]·X)·W1 + b1 : gathers f floats per non-zero instead of h
                 float* AX = nullptr;
@@ -1098,8 +1280,8 @@ extern "C" int lt_attack_efficient(const int32_t* indptr, const int32_t* indices
                 }
             }
         }
-        if (st == LT_OK) st = influence_rows(plan, HR, h, Pt, h, nullptr, W2, h, c, delta, out, ldo, s);
-        if (st == LT_OK && info_host) st = lt_plan_info(plan, h, c, info_host, stream);
+        if (st == LT_OK && !sign_path) st = influence_rows(plan, HR, h, Pt, h, nullptr, W2, h, c, delta, out, ldo, s);
+        if (st == LT_OK && !sign_path && info_host) st = lt_plan_info(plan, h, c, info_host, stream);
     }
     lt_plan_destroy(plan, stream);
     return st;

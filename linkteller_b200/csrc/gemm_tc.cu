@@ -77,4 +77,27 @@ int gemm_3xtf32(const float* A, int64_t lda, const int32_t* a_rows, const float*
     return LT_OK;
 }
 
+// sign mask + smallest magnitude per row of A·B + bias (TC_EPI_SIGN); N tiles are multiples of 32 so that a
+// 32-column group of the epilogue is one whole word of the mask
+int gemm_3xtf32_signs(const float* A, int64_t lda, const float* B, int64_t ldb, const float* bias, int32_t M, int32_t N,
+                      int32_t K, uint32_t* sign_words, uint32_t* minabs_bits, cudaStream_t s) {
+    if (M <= 0 || N <= 0 || K <= 0) return LT_OK;
+    const int nt = N <= 32 ? 32 : N <= 64 ? 64 : N <= 128 ? 128 : 256;
+    const int32_t n_pad = (N + nt - 1) / nt * nt;
+    const int32_t kchunks = (K + TC_BK - 1) / TC_BK;
+    const int32_t wpr = (N + 31) / 32;
+    Scratch scratch(s);
+    uint32_t* img;
+    LT_TRY(scratch.alloc(&img, (size_t)kchunks * 2 * n_pad * TC_BK));
+    LT_TRY(tc_prepack_b(B, ldb, 0, N, K, n_pad, img, s));
+    const PlainA prod{A, lda, nullptr};
+    switch (nt) {
+        case 32: LT_TRY((launch_tc<32, 2, PlainA, TC_EPI_SIGN>(prod, img, bias, 0, nullptr, 0, M, N, K, n_pad, kchunks, s, sign_words, wpr, minabs_bits))); break;
+        case 64: LT_TRY((launch_tc<64, 2, PlainA, TC_EPI_SIGN>(prod, img, bias, 0, nullptr, 0, M, N, K, n_pad, kchunks, s, sign_words, wpr, minabs_bits))); break;
+        case 128: LT_TRY((launch_tc<128, 1, PlainA, TC_EPI_SIGN>(prod, img, bias, 0, nullptr, 0, M, N, K, n_pad, kchunks, s, sign_words, wpr, minabs_bits))); break;
+        default: LT_TRY((launch_tc<256, 1, PlainA, TC_EPI_SIGN>(prod, img, bias, 0, nullptr, 0, M, N, K, n_pad, kchunks, s, sign_words, wpr, minabs_bits))); break;
+    }
+    return LT_OK;
+}
+
 }  // namespace lt

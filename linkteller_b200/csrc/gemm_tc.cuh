@@ -21,6 +21,15 @@ __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) 
     hi = to_tf32(x);
     lo = to_tf32(x - __uint_as_float(hi));
 }
+// The same split with the rounding done by hand: round-to-nearest (ties away from zero) to 10 mantissa bits is
+// "add half an ulp, clear the low 13 bits" on the bit pattern — two integer instructions instead of the ~6 ptxas
+// emits for cvt.rna.tf32.f32 (which also screens Inf/NaN).  Identical to split_tf32 for finite inputs; Inf stays
+// Inf, a NaN stays a NaN through the lo term.  The A-operand staging loop is issue-bound, so this matters there.
+__device__ __forceinline__ uint32_t rna_tf32_bits(float x) { return (__float_as_uint(x) + 0x1000u) & 0xffffe000u; }
+__device__ __forceinline__ void split_tf32_fast(float x, uint32_t& hi, uint32_t& lo) {
+    hi = rna_tf32_bits(x);
+    lo = rna_tf32_bits(x - __uint_as_float(hi));
+}
 
 // byte offset of element (row, k) inside a [rows x 32] K-major tile with 128-byte swizzle:
 // 8-row groups of 1024 B, 16-byte chunks XOR-ed with the row index inside the group
@@ -92,15 +101,34 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
 // A-operand producers.  A producer describes how element (row m, column k) of the A operand is
 // obtained: per-row metadata (two offsets and a scalar, kept in shared memory per tile), the raw
 // global loads for one element (prefetched one K chunk ahead) and the value computed from them.
-struct TcRaw { float x, y; };
+//   meta(m, o0, o1, f)      per-row metadata (o0 < 0 marks a row past M)
+//   raw4(o0, o1, k, K)      raw operands of elements k..k+3 (k % 4 == 0; elements at or past K must come back as 0)
+//   value(x, y, f)          the element from its raw operands and the row scalar
+struct TcRaw4 { float4 x, y; };
+
+// four consecutive floats of a row: one 16-byte load when the address allows it, bounds-checked scalars otherwise
+__device__ __forceinline__ float4 tc_load4(const float* p, int k, int K, bool vec) {
+    if (vec && k + 4 <= K) return __ldg(reinterpret_cast<const float4*>(p + k));
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (k < K) v.x = __ldg(p + k);
+    if (k + 1 < K) v.y = __ldg(p + k + 1);
+    if (k + 2 < K) v.z = __ldg(p + k + 2);
+    if (k + 3 < K) v.w = __ldg(p + k + 3);
+    return v;
+}
 
 struct PlainA {   // A[m,k] = A[a_rows ? a_rows[m] : m][k]
     const float* A; int64_t lda; const int32_t* a_rows;
+    bool vec;     // rows are 16-byte aligned (A aligned, lda % 4 == 0)
+    PlainA(const float* A_, int64_t lda_, const int32_t* a_rows_)
+        : A(A_), lda(lda_), a_rows(a_rows_), vec(lda_ % 4 == 0 && (reinterpret_cast<uintptr_t>(A_) & 15) == 0) {}
     __device__ __forceinline__ void meta(int m, int64_t& o0, int64_t& o1, float& f) const {
         o0 = (int64_t)(a_rows ? a_rows[m] : m) * lda; o1 = 0; f = 0.f;
     }
-    __device__ __forceinline__ TcRaw raw(int64_t o0, int64_t, int k) const { return TcRaw{__ldg(A + o0 + k), 0.f}; }
-    __device__ __forceinline__ float value(TcRaw r, float) const { return r.x; }
+    __device__ __forceinline__ TcRaw4 raw4(int64_t o0, int64_t, int k, int K) const {
+        return TcRaw4{tc_load4(A + o0, k, K, vec), make_float4(0.f, 0.f, 0.f, 0.f)};
+    }
+    __device__ __forceinline__ float value(float x, float, float) const { return x; }
 };
 
 struct TcSmem {
@@ -111,10 +139,18 @@ template <int NT>
 constexpr size_t tc_smem_bytes() { return (size_t)TC_STAGES * (2 * TcSmem::A_TILE + 2 * NT * TC_BK * 4) + 1024; }
 
 // C[M,N] = Aop[M,K]·B (+bias) (ReLU), B given as the packed image of k_tc_prepack_b.
-template <int NT, int MINB, class Prod>
+//
+// EPI selects what the epilogue keeps of a tile: TC_EPI_STORE writes C; TC_EPI_SIGN keeps only the sign of every
+// element — one bit per element in sign_words[m·words_per_row + col/32] — and the row's smallest magnitude
+// (atomicMin on the float bits into minabs_bits[m], pre-set to a large value), for callers that need to know
+// which ReLUs fire and how far the closest one is from switching, not the values (frontier.cu).
+constexpr int TC_EPI_STORE = 0, TC_EPI_SIGN = 1;
+
+template <int NT, int MINB, class Prod, int EPI = TC_EPI_STORE>
 __global__ void __launch_bounds__(TC_THREADS, MINB)
 k_gemm_tc(Prod prod, const uint32_t* __restrict__ Bimg, const float* __restrict__ bias, int relu, float* __restrict__ C,
-          int64_t ldc, int32_t M, int32_t N, int32_t K, int32_t n_pad_total, int32_t kchunks) {
+          int64_t ldc, int32_t M, int32_t N, int32_t K, int32_t n_pad_total, int32_t kchunks,
+          uint32_t* __restrict__ sign_words = nullptr, int32_t words_per_row = 0, uint32_t* __restrict__ minabs_bits = nullptr) {
     constexpr int B_TILE = NT * TC_BK * 4;
     constexpr int STAGE = 2 * TcSmem::A_TILE + 2 * B_TILE;
     constexpr int TMEM_COLS = NT <= 32 ? 32 : NT <= 64 ? 64 : NT <= 128 ? 128 : 256;
@@ -157,16 +193,21 @@ k_gemm_tc(Prod prod, const uint32_t* __restrict__ Bimg, const float* __restrict_
     const uint32_t tmem_base = tmem_base_s;
     constexpr uint32_t idesc = make_idesc(TC_BM, NT);
 
-    // raw operands of the NEXT chunk, prefetched while the tensor core works on the current one:
-    // this warp stages rows warp*16 .. +15, lane ↔ k inside the chunk
-    TcRaw pre[16];
+    // raw operands of the NEXT chunk, prefetched while the tensor core works on the current one.
+    // This warp stages rows warp*16 .. +15; a lane owns FOUR consecutive k of four rows (row sub-index lane/8,
+    // 16-byte group lane%8), so one 16-byte load per operand and one 16-byte shared store per hi / lo image
+    // cover four elements — the staging loop was instruction-issue bound with one element per load and store
+    // (ncu r1g: issue slots 50 % busy, tensor pipe 7 %).
+    TcRaw4 pre[4];
+    const int st_row = warp * 16 + (lane >> 3), st_k4 = lane & 7;
     auto prefetch = [&](int tile_idx, int kc) {
-        const int k = kc * TC_BK + lane;
+        const int k = kc * TC_BK + st_k4 * 4;
         const int b = tile_idx & 1;
 #pragma unroll
-        for (int q = 0; q < 16; ++q) {
-            const int64_t o0 = meta0[b][warp * 16 + q];
-            pre[q] = (o0 >= 0 && k < K) ? prod.raw(o0, meta1[b][warp * 16 + q], k) : TcRaw{0.f, 0.f};
+        for (int i = 0; i < 4; ++i) {
+            const int64_t o0 = meta0[b][st_row + 4 * i];
+            if (o0 >= 0 && k < K) pre[i] = prod.raw4(o0, meta1[b][st_row + 4 * i], k, K);
+            else pre[i] = TcRaw4{make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
         }
     };
     const uint32_t total = (uint32_t)my_tiles * (uint32_t)kchunks;
@@ -195,13 +236,17 @@ k_gemm_tc(Prod prod, const uint32_t* __restrict__ Bimg, const float* __restrict_
         {
             const int b = tile_idx & 1;
 #pragma unroll
-            for (int q = 0; q < 16; ++q) {
-                const float v = prod.value(pre[q], meta2[b][warp * 16 + q]);
-                uint32_t hi, lo;
-                split_tf32(v, hi, lo);
-                const uint32_t off = sw128_offset(warp * 16 + q, lane);
-                *reinterpret_cast<uint32_t*>(a_hi + off) = hi;
-                *reinterpret_cast<uint32_t*>(a_lo + off) = lo;
+            for (int i = 0; i < 4; ++i) {
+                const int r = st_row + 4 * i;
+                const float a = meta2[b][r];
+                uint4 hi, lo;
+                split_tf32_fast(prod.value(pre[i].x.x, pre[i].y.x, a), hi.x, lo.x);
+                split_tf32_fast(prod.value(pre[i].x.y, pre[i].y.y, a), hi.y, lo.y);
+                split_tf32_fast(prod.value(pre[i].x.z, pre[i].y.z, a), hi.z, lo.z);
+                split_tf32_fast(prod.value(pre[i].x.w, pre[i].y.w, a), hi.w, lo.w);
+                const uint32_t off = sw128_offset(r, st_k4 * 4);      // one whole 16-byte group of the swizzled row
+                *reinterpret_cast<uint4*>(a_hi + off) = hi;
+                *reinterpret_cast<uint4*>(a_lo + off) = lo;
             }
         }
         if (kc == 0) load_meta(tile_idx + 1);                // visible after this iteration's barrier
@@ -252,6 +297,24 @@ k_gemm_tc(Prod prod, const uint32_t* __restrict__ Bimg, const float* __restrict_
                     uint32_t v[32];
                     tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
                     const int lim = min((half + 1) * COLS_PER_HALF - c0, 32);   // valid columns of this load
+                    if (EPI == TC_EPI_SIGN) {
+                        // lane = row: its 32 columns make exactly one word of the row's sign mask
+                        uint32_t word = 0;
+                        float mn = __uint_as_float(0x7f7f7f7fu);
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float x = __uint_as_float(v[j]) + bias_s[c0 + j];
+                            if (j < lim && n0 + c0 + j < N) {
+                                word |= (x > 0.f ? 1u : 0u) << j;
+                                mn = fminf(mn, fabsf(x));
+                            }
+                        }
+                        const int m = m_base + lane;
+                        if (m < M && n0 + c0 < N) {
+                            sign_words[(int64_t)m * words_per_row + ((n0 + c0) >> 5)] = word;
+                            atomicMin(minabs_bits + m, __float_as_uint(mn));
+                        }
+                    } else {
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
                         // bias from shared memory (one broadcast float4 per four columns)
@@ -282,6 +345,7 @@ k_gemm_tc(Prod prod, const uint32_t* __restrict__ Bimg, const float* __restrict_
                         }
                     }
                     __syncwarp();
+                    }
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -298,18 +362,19 @@ k_gemm_tc(Prod prod, const uint32_t* __restrict__ Bimg, const float* __restrict_
 }
 
 // launch over M tiles (persistent CTAs) x N tiles; img = packed B of k_tc_prepack_b
-template <int NT, int MINB, class Prod>
+template <int NT, int MINB, class Prod, int EPI = TC_EPI_STORE>
 static int launch_tc(const Prod& prod, const uint32_t* img, const float* bias, int relu, float* C, int64_t ldc, int32_t M,
-                     int32_t N, int32_t K, int32_t n_pad, int32_t kchunks, cudaStream_t s) {
+                     int32_t N, int32_t K, int32_t n_pad, int32_t kchunks, cudaStream_t s, uint32_t* sign_words = nullptr,
+                     int32_t words_per_row = 0, uint32_t* minabs_bits = nullptr) {
     const size_t smem = tc_smem_bytes<NT>();
-    LT_CUDA(cudaFuncSetAttribute(k_gemm_tc<NT, MINB, Prod>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LT_CUDA(cudaFuncSetAttribute(k_gemm_tc<NT, MINB, Prod, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int tiles_m = (M + TC_BM - 1) / TC_BM;
     const int n_tiles = n_pad / NT;
     int gx = num_sms() * MINB / n_tiles;
     if (gx < 1) gx = 1;
     if (gx > tiles_m) gx = tiles_m;
-    k_gemm_tc<NT, MINB, Prod><<<dim3((unsigned)gx, (unsigned)n_tiles), TC_THREADS, smem, s>>>(prod, img, bias, relu, C, ldc, M,
-                                                                                            N, K, n_pad, kchunks);
+    k_gemm_tc<NT, MINB, Prod, EPI><<<dim3((unsigned)gx, (unsigned)n_tiles), TC_THREADS, smem, s>>>(
+        prod, img, bias, relu, C, ldc, M, N, K, n_pad, kchunks, sign_words, words_per_row, minabs_bits);
     LT_LAUNCH_CHECK();
     return LT_OK;
 }
@@ -322,5 +387,8 @@ static inline int tc_pick_nt(int N) {
 }
 
 int tc_prepack_b(const float* B, int64_t ldb, int transB, int32_t N, int32_t K, int32_t n_pad, uint32_t* img, cudaStream_t s);
+// signs of A[M,K]·B + bias: sign_words [M, (N+31)/32] and minabs_bits [M] (caller pre-sets them to 0x7f7f7f7f); gemm_tc.cu
+int gemm_3xtf32_signs(const float* A, int64_t lda, const float* B, int64_t ldb, const float* bias, int32_t M, int32_t N,
+                      int32_t K, uint32_t* sign_words, uint32_t* minabs_bits, cudaStream_t s);
 
 }  // namespace lt

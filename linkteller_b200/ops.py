@@ -272,7 +272,7 @@ def model_forward(adj: DeviceCSR, x, weights) -> torch.Tensor:
 
 # ------------------------------------------------------------------------------------------ a7/a8
 INFO_KEYS = ("frontier_rows", "incidences", "observer_entries", "records", "support_pairs", "frontier_bytes",
-             "frontier_row_nnz", "reserved")
+             "frontier_row_nnz", "exact_path_incidences")
 
 
 def attack_efficient(adj: DeviceCSR, x, w1, b1, w2, test_nodes: torch.Tensor, delta: float,

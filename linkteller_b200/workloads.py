@@ -101,8 +101,11 @@ def degree_thresholds(dataset: str):
 
 
 def make(name: str, device="cuda", seed: int = 0, hidden: int = 256, delta: float = 1e-4,
-         norm: str = "FirstOrderGCN", n_test: Optional[int] = None, sample_seed: int = 42) -> Workload:
-    cfg = synth.SHAPES[name]
+         norm: str = "FirstOrderGCN", n_test: Optional[int] = None, sample_seed: int = 42,
+         f: Optional[int] = None) -> Workload:
+    cfg = dict(synth.SHAPES[name])
+    if f is not None:
+        cfg["f"] = f                                  # feature-width override (tests of the width-dependent paths)
     n, f, c = cfg["n"], cfg["f"], cfg["c"]
     T = n_test or cfg["T"]
     if name == "large":
@@ -114,7 +117,7 @@ def make(name: str, device="cuda", seed: int = 0, hidden: int = 256, delta: floa
         x = torch.randn((n, f), generator=g, device=device, dtype=torch.float32)
         tn = sample_test_nodes(n, T, sample_seed)
     else:
-        s = synth.make(name, seed=seed, hidden=hidden)
+        s = synth.make(name, seed=seed, hidden=hidden, f=f)
         adj = ops.csr_from_edges(torch.from_numpy(s.edges).to(device), n)
         x = torch.from_numpy(s.features).to(device)
         tn = sample_test_nodes_typed(cfg["dataset"], cfg["sample_type"], adj.indptr.cpu().numpy(), T, sample_seed)

@@ -54,3 +54,29 @@ def test_config_flickr():
     from linkteller_b200 import workloads
     wl = workloads.make("flickr")
     check_rows(wl, [0, 777, 1999])
+
+
+def test_sign_mask_path_matches_value_path_and_oracle(monkeypatch):
+    """lt_attack_efficient keeps only the signs of H_R (one bit per element + the row's smallest magnitude) when
+    the products run on the tensor cores.  Rows where no ReLU can switch give the bits of the value path; rows
+    where one can are recomputed exactly.  A large δ forces many such rows."""
+    from linkteller_b200 import ops, workloads
+    for delta, min_exact in ((1e-4, 0), (3e-2, 100)):
+        wl = workloads.make("ppi", delta=delta, f=52)       # f % 4 == 0 and f < h: aggregate-first precompute
+        monkeypatch.delenv("LT_NO_SIGN_PATH", raising=False)
+        with ops.profile() as prof:
+            a, info = ops.attack_efficient(wl.adj_hat, wl.x, wl.w1, wl.b1, wl.w2, wl.test_nodes, wl.delta, want_info=True)
+        assert "gemm_h" in prof.report() and "frontier_dq" in prof.report()
+        assert info["exact_path_incidences"] >= min_exact
+        monkeypatch.setenv("LT_NO_SIGN_PATH", "1")
+        b, info_b = ops.attack_efficient(wl.adj_hat, wl.x, wl.w1, wl.b1, wl.w2, wl.test_nodes, wl.delta, want_info=True)
+        assert info_b["exact_path_incidences"] == 0
+        monkeypatch.delenv("LT_NO_SIGN_PATH")
+        a, b = a.cpu().numpy(), b.cpu().numpy()
+        assert np.array_equal(a == 0, b == 0)
+        nz = b != 0
+        rel = np.abs(a[nz] - b[nz]) / np.abs(b[nz])
+        assert rel.max() <= 1e-3, rel.max()   # a switching ReLU contributes −H/δ: two fp32 evaluations of H differ by ~1e-7/δ there
+        if info["exact_path_incidences"] == 0:
+            assert np.array_equal(a, b)                 # same A operand, same GEMM: same bits
+        check_rows(wl, range(3, 500, 45))               # and the float64 oracle, at this δ
