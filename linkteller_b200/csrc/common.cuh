@@ -97,6 +97,10 @@ static inline int bits_for(uint64_t max_value) {  // number of bits needed to re
 // ---- device helpers ----
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 
+__device__ __forceinline__ void fma4(float4& a, float v, const float4& x) {
+    a.x = fmaf(v, x.x, a.x); a.y = fmaf(v, x.y, a.y); a.z = fmaf(v, x.z, a.z); a.w = fmaf(v, x.w, a.w);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(LT_FULL, v, o);

@@ -450,66 +450,93 @@ __global__ void k_row_absmax(const float* __restrict__ P, int64_t ldp, int32_t r
     if (lane == 0) pmax[j] = m;
 }
 
-// One warp per incidence.  Rows whose smallest |H| cannot be crossed by the perturbation return at once (the
-// masked product is exact for them).  For the others H[r,:] = AX[r,:]·W1 + b1 is recomputed in fp32 (a lane owns
-// the hidden units lane, lane+32, …: up to eight independent accumulators, W1 rows read coalesced), ΔR is
-// evaluated case by case as in DeltaRProd, and the difference to the masked value — non-zero only where a ReLU
-// switches — is pushed through W2 into ΔQ[e,:].
-__global__ void __launch_bounds__(256)
-k_flip_fix(const int32_t* __restrict__ s_j, const int32_t* __restrict__ s_rho, const float* __restrict__ s_a, int64_t E,
-           const float* __restrict__ AX, int64_t ldax, int32_t f, const float* __restrict__ W1, const float* __restrict__ b1,
-           const float* __restrict__ P, int64_t ldp, const int32_t* __restrict__ p_index, const float* __restrict__ pmax,
-           const uint32_t* __restrict__ sign_words, int32_t wpr, const uint32_t* __restrict__ minabs_bits,
-           const float* __restrict__ W2, int32_t h, int32_t c, float delta, float inv_delta, float* __restrict__ dq,
-           int32_t lddq, int32_t* __restrict__ n_fixed) {
-    const int lane = threadIdx.x & 31;
-    const int64_t e = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+// One thread per incidence: queue those whose row has an |H| small enough for a ReLU to switch under this
+// perturbation (|H| ≤ |δ·a|·max|P[v]|, with a margin for the rounding of the bound itself).  The order of the queue
+// does not matter: every entry patches its own ΔQ row.
+__global__ void k_slow_mark(const int32_t* __restrict__ s_j, const int32_t* __restrict__ s_rho, const float* __restrict__ s_a,
+                            int64_t E, const uint32_t* __restrict__ minabs_bits, const float* __restrict__ pmax, float delta,
+                            int32_t* __restrict__ slow_list, int32_t* __restrict__ n_slow) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= E) return;
-    const int32_t j = s_j[e], rho = s_rho[e];
-    const float a = s_a[e];
-    const float thr = fabsf(delta * a) * pmax[j] * 1.001f;
-    if (__uint_as_float(minabs_bits[rho]) > thr) return;
-    if (lane == 0 && n_fixed) atomicAdd(n_fixed, 1);
-    const float* ax = AX + (int64_t)rho * ldax;
-    const float* prow = P + (int64_t)(p_index ? p_index[j] : j) * ldp;
-    const float da = delta * a;
-    for (int k0 = 0; k0 < h; k0 += 256) {
-        float hh[8];
+    const float thr = fabsf(delta * s_a[e]) * pmax[s_j[e]] * 1.001f;
+    if (!(__uint_as_float(minabs_bits[s_rho[e]]) > thr)) slow_list[atomicAdd(n_slow, 1)] = (int32_t)e;
+}
+
+// The queued incidences, one warp each,
+// grid-stride over the queue.  H[r,:] = AX[r,:]·W1 + b1 is recomputed in fp32 (a lane owns the hidden units lane,
+// lane+32, …: up to eight independent accumulators, W1 rows read coalesced), ΔR is evaluated case by case as in
+// DeltaRProd, and the difference to the masked value — non-zero only where a ReLU switches — is pushed through W2
+// into ΔQ[e,:].
+__global__ void __launch_bounds__(256)
+k_flip_fix(const int32_t* __restrict__ slow_list, const int32_t* __restrict__ n_slow, const int32_t* __restrict__ s_j,
+           const int32_t* __restrict__ s_rho, const float* __restrict__ s_a, const float* __restrict__ AX, int64_t ldax,
+           int32_t f, const float* __restrict__ W1, const float* __restrict__ b1, const float* __restrict__ P, int64_t ldp,
+           const int32_t* __restrict__ p_index, const uint32_t* __restrict__ sign_words, int32_t wpr,
+           const float* __restrict__ W2, int32_t h, int32_t c, float delta, float inv_delta, float* __restrict__ dq,
+           int32_t lddq) {
+    const int lane = threadIdx.x & 31;
+    const int32_t total = *n_slow;
+    const int32_t stride = (int32_t)((gridDim.x * blockDim.x) >> 5);
+    for (int32_t q = (int32_t)((blockIdx.x * blockDim.x + threadIdx.x) >> 5); q < total; q += stride) {
+        const int64_t e = slow_list[q];
+        const int32_t j = s_j[e], rho = s_rho[e];
+        const float a = s_a[e];
+        const float* ax = AX + (int64_t)rho * ldax;
+        const float* prow = P + (int64_t)(p_index ? p_index[j] : j) * ldp;
+        const float da = delta * a;
+        // hidden units of this lane inside a block of 256: 4·lane … +3 and 128 + 4·lane … +3 (h % 4 == 0), so a W1
+        // row costs two 16-byte loads per lane; eight rows are fetched before their 64 FMAs — loaded one scalar at a
+        // time and consumed at once, the 800 dependent loads of an entry took 150 µs (ncu r1j: FFMA on long_scoreboard)
+        for (int k0 = 0; k0 < h; k0 += 256) {
+            const int ka = k0 + 4 * lane, kb2 = k0 + 128 + 4 * lane;
+            const bool va = ka < h, vb = kb2 < h;
+            float4 ha = va ? make_float4(b1[ka], b1[ka + 1], b1[ka + 2], b1[ka + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 hb = vb ? make_float4(b1[kb2], b1[kb2 + 1], b1[kb2 + 2], b1[kb2 + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const int ca = va ? ka : 0, cb = vb ? kb2 : 0;                 // clamped columns: loads stay unconditional
+            for (int i0 = 0; i0 < f; i0 += 32) {
+                const float av = i0 + lane < f ? ax[i0 + lane] : 0.f;      // 32 entries of the AX row, one per lane
+                for (int u0 = 0; u0 < 32 && i0 + u0 < f; u0 += 8) {
+                    float4 wa[8], wb[8];
 #pragma unroll
-        for (int t = 0; t < 8; ++t) { const int k = k0 + lane + 32 * t; hh[t] = k < h ? b1[k] : 0.f; }
-        for (int i0 = 0; i0 < f; i0 += 32) {
-            const float av = i0 + lane < f ? ax[i0 + lane] : 0.f;          // 32 entries of the AX row, one per lane
-            const int cnt = min(32, f - i0);
-            for (int u = 0; u < cnt; ++u) {
-                const float ai = __shfl_sync(LT_FULL, av, u);
-                const float* w1 = W1 + (int64_t)(i0 + u) * h + k0 + lane;
+                    for (int u = 0; u < 8; ++u) {
+                        const int i = min(i0 + u0 + u, f - 1);             // rows past f: re-read the last row, weight 0
+                        wa[u] = __ldg(reinterpret_cast<const float4*>(W1 + (int64_t)i * h + ca));
+                        wb[u] = __ldg(reinterpret_cast<const float4*>(W1 + (int64_t)i * h + cb));
+                    }
 #pragma unroll
-                for (int t = 0; t < 8; ++t)
-                    if (k0 + lane + 32 * t < h) hh[t] = fmaf(ai, __ldg(w1 + 32 * t), hh[t]);
+                    for (int u = 0; u < 8; ++u) {
+                        const float ai = __shfl_sync(LT_FULL, av, u0 + u);  // 0 for rows past f
+                        fma4(ha, ai, wa[u]);
+                        fma4(hb, ai, wb[u]);
+                    }
+                }
             }
-        }
+            const float hs[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
 #pragma unroll
-        for (int t = 0; t < 8; ++t) {
-            const int kb = k0 + 32 * t;                                    // warp-uniform
-            if (kb >= h) break;
-            const int k = kb + lane;
-            float d = 0.f;
-            if (k < h) {
-                const float p = prow[k];
-                const float hp = fmaf(da, p, hh[t]);
-                float exact;
-                if (hh[t] > 0.f) exact = hp > 0.f ? a * p : -hh[t] * inv_delta;
-                else exact = hp > 0.f ? hp * inv_delta : 0.f;
-                const uint32_t bit = (sign_words[(int64_t)rho * wpr + (k >> 5)] >> (k & 31)) & 1u;
-                d = exact - (bit ? a * p : 0.f);
-            }
-            uint32_t m = __ballot_sync(LT_FULL, d != 0.f);
-            while (m) {
-                const int src = __ffs(m) - 1;
-                m &= m - 1;
-                const float dk = __shfl_sync(LT_FULL, d, src);
-                const float* w2 = W2 + (int64_t)(kb + src) * c;
-                for (int col = lane; col < c; col += 32) dq[e * lddq + col] = fmaf(dk, w2[col], dq[e * lddq + col]);
+            for (int t = 0; t < 8; ++t) {
+                const int k = (t < 4 ? ka : kb2) + (t & 3);
+                float d = 0.f;
+                if (k < h) {
+                    const float p = prow[k];
+                    const float hp = fmaf(da, p, hs[t]);
+                    // one rounded product for both terms: written as a·p twice, the compiler may contract the
+                    // subtraction into an fma and d becomes the product's rounding error instead of 0
+                    const float ap = __fmul_rn(a, p);
+                    float exact;
+                    if (hs[t] > 0.f) exact = hp > 0.f ? ap : -hs[t] * inv_delta;
+                    else exact = hp > 0.f ? hp * inv_delta : 0.f;
+                    const uint32_t bit = (sign_words[(int64_t)rho * wpr + (k >> 5)] >> (k & 31)) & 1u;
+                    d = exact - (bit ? ap : 0.f);
+                }
+                uint32_t m = __ballot_sync(LT_FULL, d != 0.f);
+                while (m) {
+                    const int src = __ffs(m) - 1;
+                    m &= m - 1;
+                    const float dk = __shfl_sync(LT_FULL, d, src);
+                    const int ks = (t < 4 ? k0 + 4 * src : k0 + 128 + 4 * src) + (t & 3);
+                    const float* w2 = W2 + (int64_t)ks * c;
+                    for (int col = lane; col < c; col += 32) dq[e * lddq + col] = fmaf(dk, w2[col], dq[e * lddq + col]);
+                }
             }
         }
     }
@@ -727,7 +754,9 @@ static int frontier_dq_signs(const lt_plan* p, const uint32_t* sign_words, int32
     Scratch scratch(s);
     const int32_t lddq = frontier_lddq(E, h, c);
     float* pmax;
+    int32_t* slow_list;
     LT_TRY(scratch.alloc(&pmax, (size_t)p->Ts));
+    LT_TRY(scratch.alloc(&slow_list, (size_t)E));
     ProfScope prof("frontier_dq", s);
     k_row_absmax<<<(unsigned)ceil_div((int64_t)p->Ts * 32, 256), 256, 0, s>>>(P, ldp, p->Ts, h, pmax);
     LT_LAUNCH_CHECK();
@@ -736,6 +765,8 @@ static int frontier_dq_signs(const lt_plan* p, const uint32_t* sign_words, int32
     uint32_t* img;
     LT_TRY(scratch.alloc(&img, (size_t)kchunks * 2 * n_pad * TC_BK));
     LT_TRY(tc_prepack_b(W2, c, 0, c, h, n_pad, img, s));
+    k_slow_mark<<<(unsigned)ceil_div(E, 256), 256, 0, s>>>(p->s_j, p->s_rho, p->s_a, E, minabs_bits, pmax, delta, slow_list, n_fixed);
+    LT_LAUNCH_CHECK();
     const MaskProd prod{p->s_j, p->s_rho, p->s_a, p_index, sign_words, wpr, P, ldp};
     switch (nt) {
         case 32: LT_TRY((launch_tc<32, 2>(prod, img, nullptr, 0, dq, lddq, (int32_t)E, c, h, n_pad, kchunks, s))); break;
@@ -744,9 +775,8 @@ static int frontier_dq_signs(const lt_plan* p, const uint32_t* sign_words, int32
         case 128: LT_TRY((launch_tc<128, 1>(prod, img, nullptr, 0, dq, lddq, (int32_t)E, c, h, n_pad, kchunks, s))); break;
         default: LT_TRY((launch_tc<256, 1>(prod, img, nullptr, 0, dq, lddq, (int32_t)E, c, h, n_pad, kchunks, s))); break;
     }
-    k_flip_fix<<<(unsigned)ceil_div(E * 32, 256), 256, 0, s>>>(p->s_j, p->s_rho, p->s_a, E, AX, ldax, f, W1, b1, P, ldp, p_index,
-                                                               pmax, sign_words, wpr, minabs_bits, W2, h, c, delta, 1.0f / delta, dq,
-                                                               lddq, n_fixed);
+    k_flip_fix<<<(unsigned)num_sms() * 2, 256, 0, s>>>(slow_list, n_fixed, p->s_j, p->s_rho, p->s_a, AX, ldax, f, W1, b1, P, ldp,
+                                                       p_index, sign_words, wpr, W2, h, c, delta, 1.0f / delta, dq, lddq);
     LT_LAUNCH_CHECK();
     return LT_OK;
 }
@@ -1208,7 +1238,8 @@ extern "C" int lt_attack_efficient(const int32_t* indptr, const int32_t* indices
         // sign-mask path: H_R is never written — the GEMM keeps one bit per element and the row's smallest magnitude
         // (36 bytes per frontier row instead of 4h), F1 reads those, and the rows where a ReLU can switch are patched
         const bool sign_path = aggregate_first && frontier_use_tc(plan->E, h, c) && h >= 16 &&
-                               (int64_t)R * h * f >= ((int64_t)1 << 24) && plan->M > 0 && !getenv("LT_NO_SIGN_PATH");
+                               (int64_t)R * h * f >= ((int64_t)1 << 24) && plan->M > 0 && (uintptr_t)W1 % 16 == 0 &&
+                               !getenv("LT_NO_SIGN_PATH");
         if (st == LT_OK && sign_path) {
             float* AX = nullptr;
             uint32_t *signs = nullptr, *minabs = nullptr;

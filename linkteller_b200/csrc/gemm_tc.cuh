@@ -257,8 +257,10 @@ k_gemm_tc(Prod prod, const uint32_t* __restrict__ Bimg, const float* __restrict_
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint64_t da_hi = make_smem_desc(smem_u32(a_hi)), da_lo = make_smem_desc(smem_u32(a_lo));
             const uint64_t db_hi = make_smem_desc(smem_u32(b_hi)), db_lo = make_smem_desc(smem_u32(b_hi + B_TILE));
+            const int ksteps = min(TC_BK / 8, (K - kc * TC_BK + 7) / 8);   // K steps past K multiply zeros: not issued
 #pragma unroll
             for (int ks = 0; ks < TC_BK / 8; ++ks) {
+                if (ks >= ksteps) break;
                 const uint64_t adv = (uint64_t)((ks * 8 * 4) >> 4);     // +32 bytes per K step inside the swizzle atom
                 umma_tf32(tmem_base, da_hi + adv, db_hi + adv, idesc, (kc | ks) ? 1u : 0u);
                 umma_tf32(tmem_base, da_hi + adv, db_lo + adv, idesc, 1u);

@@ -33,9 +33,6 @@ __global__ void k_spmm_segcount(const int32_t* __restrict__ indptr, const int32_
     nseg[t] = len <= seg ? 1 : (len + seg - 1) / seg;
 }
 
-__device__ __forceinline__ void fma4(float4& a, float v, const float4& x) {
-    a.x = fmaf(v, x.x, a.x); a.y = fmaf(v, x.y, a.y); a.z = fmaf(v, x.z, a.z); a.w = fmaf(v, x.w, a.w);
-}
 
 // NV = float4 slices per lane (d ≤ 128·NV).  seg_off: exclusive scan of nseg (n_rows+1 entries).
 // The (column, value) pairs of the NEXT 32 non-zeros are loaded before the gathers of the current 32 are
