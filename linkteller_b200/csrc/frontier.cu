@@ -405,14 +405,20 @@ struct DeltaRProd {
         o1 = (int64_t)(p_index ? p_index[j] : j) * ldp;
         f = s_a[e];
     }
+    struct Raw { float4 h, p; };
+    static constexpr int PD = 1;      // two Raw sets (64 registers) would not fit two CTAs per SM
     // h, ldh, ldp are multiples of 4 and H, P 16-byte aligned (checked by frontier_dq): always one 16-byte load each
-    __device__ __forceinline__ TcRaw4 raw4(int64_t o0, int64_t o1, int k, int) const {
-        return TcRaw4{__ldg(reinterpret_cast<const float4*>(H + o0 + k)), __ldg(reinterpret_cast<const float4*>(P + o1 + k))};
+    __device__ __forceinline__ Raw raw4(int64_t o0, int64_t o1, int k, int) const {
+        return Raw{__ldg(reinterpret_cast<const float4*>(H + o0 + k)), __ldg(reinterpret_cast<const float4*>(P + o1 + k))};
     }
+    __device__ __forceinline__ Raw zero() const { return Raw{make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)}; }
     __device__ __forceinline__ float value(float hh, float p, float a) const {
         const float hp = fmaf(delta * a, p, hh);           // H'[r,k]
         if (hh > 0.f) return hp > 0.f ? a * p : -hh * inv_delta;
         return hp > 0.f ? hp * inv_delta : 0.f;
+    }
+    __device__ __forceinline__ float4 value4(const Raw& r, float a) const {
+        return make_float4(value(r.h.x, r.p.x, a), value(r.h.y, r.p.y, a), value(r.h.z, r.p.z, a), value(r.h.w, r.p.w, a));
     }
 };
 
@@ -429,13 +435,16 @@ struct MaskProd {
         o1 = (int64_t)(p_index ? p_index[j] : j) * ldp;
         f = s_a[e];
     }
-    __device__ __forceinline__ TcRaw4 raw4(int64_t o0, int64_t o1, int k, int) const {
-        const uint32_t w = __ldg(sign_words + o0 + (k >> 5)) >> (k & 31);
-        return TcRaw4{__ldg(reinterpret_cast<const float4*>(P + o1 + k)),
-                      make_float4(__uint_as_float(w & 1u), __uint_as_float((w >> 1) & 1u), __uint_as_float((w >> 2) & 1u),
-                                  __uint_as_float((w >> 3) & 1u))};
+    struct Raw { float4 p; uint32_t bits; };
+    static constexpr int PD = 2;
+    __device__ __forceinline__ Raw raw4(int64_t o0, int64_t o1, int k, int) const {
+        return Raw{__ldg(reinterpret_cast<const float4*>(P + o1 + k)), __ldg(sign_words + o0 + (k >> 5)) >> (k & 31)};
     }
-    __device__ __forceinline__ float value(float p, float bit, float a) const { return __float_as_uint(bit) ? a * p : 0.f; }
+    __device__ __forceinline__ Raw zero() const { return Raw{make_float4(0.f, 0.f, 0.f, 0.f), 0u}; }
+    __device__ __forceinline__ float4 value4(const Raw& r, float a) const {
+        return make_float4((r.bits & 1u) ? a * r.p.x : 0.f, (r.bits & 2u) ? a * r.p.y : 0.f, (r.bits & 4u) ? a * r.p.z : 0.f,
+                           (r.bits & 8u) ? a * r.p.w : 0.f);
+    }
 };
 
 // pmax[j] = max_k |P[j,k]|; one warp per row
@@ -708,7 +717,7 @@ static int frontier_dq(const lt_plan* p, const int32_t* h_index, const float* H,
     if (use_tc) {
         ProfScope prof("frontier_dq", s);
         const int nt = tc_pick_nt(c);
-        const int32_t n_pad = nt, kchunks = (h + TC_BK - 1) / TC_BK;
+        const int32_t n_pad = nt, kchunks = tc_kchunks(h);
         uint32_t* img;
         LT_TRY(scratch.alloc(&img, (size_t)kchunks * 2 * n_pad * TC_BK));
         LT_TRY(tc_prepack_b(W2, c, 0, c, h, n_pad, img, s));
@@ -761,7 +770,7 @@ static int frontier_dq_signs(const lt_plan* p, const uint32_t* sign_words, int32
     k_row_absmax<<<(unsigned)ceil_div((int64_t)p->Ts * 32, 256), 256, 0, s>>>(P, ldp, p->Ts, h, pmax);
     LT_LAUNCH_CHECK();
     const int nt = tc_pick_nt(c);
-    const int32_t n_pad = nt, kchunks = (h + TC_BK - 1) / TC_BK;
+    const int32_t n_pad = nt, kchunks = tc_kchunks(h);
     uint32_t* img;
     LT_TRY(scratch.alloc(&img, (size_t)kchunks * 2 * n_pad * TC_BK));
     LT_TRY(tc_prepack_b(W2, c, 0, c, h, n_pad, img, s));

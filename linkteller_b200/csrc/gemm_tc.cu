@@ -44,7 +44,7 @@ __global__ void k_tc_prepack_b(const float* __restrict__ B, int64_t ldb, int tra
 }
 
 int tc_prepack_b(const float* B, int64_t ldb, int transB, int32_t N, int32_t K, int32_t n_pad, uint32_t* img, cudaStream_t s) {
-    const int32_t kchunks = (K + TC_BK - 1) / TC_BK;
+    const int32_t kchunks = tc_kchunks(K);
     k_tc_prepack_b<<<(unsigned)ceil_div((int64_t)kchunks * n_pad * TC_BK, 256), 256, 0, s>>>(B, ldb, transB, N, K, n_pad,
                                                                                           kchunks, img);
     LT_LAUNCH_CHECK();
@@ -60,7 +60,7 @@ int gemm_3xtf32(const float* A, int64_t lda, const int32_t* a_rows, const float*
     if (!force && ((int64_t)M * N * K < (int64_t)1 << 24 || N < 16)) return LT_OK;
     const int nt = tc_pick_nt(N);
     const int32_t n_pad = (N + nt - 1) / nt * nt;
-    const int32_t kchunks = (K + TC_BK - 1) / TC_BK;
+    const int32_t kchunks = tc_kchunks(K);
     Scratch scratch(s);
     uint32_t* img;
     LT_TRY(scratch.alloc(&img, (size_t)kchunks * 2 * n_pad * TC_BK));
@@ -84,7 +84,7 @@ int gemm_3xtf32_signs(const float* A, int64_t lda, const float* B, int64_t ldb, 
     if (M <= 0 || N <= 0 || K <= 0) return LT_OK;
     const int nt = N <= 32 ? 32 : N <= 64 ? 64 : N <= 128 ? 128 : 256;
     const int32_t n_pad = (N + nt - 1) / nt * nt;
-    const int32_t kchunks = (K + TC_BK - 1) / TC_BK;
+    const int32_t kchunks = tc_kchunks(K);
     const int32_t wpr = (N + 31) / 32;
     Scratch scratch(s);
     uint32_t* img;

@@ -3,6 +3,8 @@
 #pragma once
 #include "common.cuh"
 
+#include <type_traits>
+
 namespace lt {
 
 constexpr int TC_BM = 128;        // rows per tile = UMMA M (cta_group::1)
@@ -102,10 +104,10 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
 // obtained: per-row metadata (two offsets and a scalar, kept in shared memory per tile), the raw
 // global loads for one element (prefetched one K chunk ahead) and the value computed from them.
 //   meta(m, o0, o1, f)      per-row metadata (o0 < 0 marks a row past M)
-//   raw4(o0, o1, k, K)      raw operands of elements k..k+3 (k % 4 == 0; elements at or past K must come back as 0)
-//   value(x, y, f)          the element from its raw operands and the row scalar
-struct TcRaw4 { float4 x, y; };
-
+//   Raw, raw4(o0, o1, k, K) raw operands of elements k..k+3 (k % 4 == 0; elements at or past K must come back as 0)
+//   zero()                  the Raw of four zero elements
+//   value4(raw, f)          the four elements from their raw operands and the row scalar
+//   PD                      prefetch distance in K chunks (1 or 2): how many Raw sets are kept in registers
 // four consecutive floats of a row: one 16-byte load when the address allows it, bounds-checked scalars otherwise
 __device__ __forceinline__ float4 tc_load4(const float* p, int k, int K, bool vec) {
     if (vec && k + 4 <= K) return __ldg(reinterpret_cast<const float4*>(p + k));
@@ -120,15 +122,16 @@ __device__ __forceinline__ float4 tc_load4(const float* p, int k, int K, bool ve
 struct PlainA {   // A[m,k] = A[a_rows ? a_rows[m] : m][k]
     const float* A; int64_t lda; const int32_t* a_rows;
     bool vec;     // rows are 16-byte aligned (A aligned, lda % 4 == 0)
+    using Raw = float4;
+    static constexpr int PD = 2;
     PlainA(const float* A_, int64_t lda_, const int32_t* a_rows_)
         : A(A_), lda(lda_), a_rows(a_rows_), vec(lda_ % 4 == 0 && (reinterpret_cast<uintptr_t>(A_) & 15) == 0) {}
     __device__ __forceinline__ void meta(int m, int64_t& o0, int64_t& o1, float& f) const {
         o0 = (int64_t)(a_rows ? a_rows[m] : m) * lda; o1 = 0; f = 0.f;
     }
-    __device__ __forceinline__ TcRaw4 raw4(int64_t o0, int64_t, int k, int K) const {
-        return TcRaw4{tc_load4(A + o0, k, K, vec), make_float4(0.f, 0.f, 0.f, 0.f)};
-    }
-    __device__ __forceinline__ float value(float x, float, float) const { return x; }
+    __device__ __forceinline__ Raw raw4(int64_t o0, int64_t, int k, int K) const { return tc_load4(A + o0, k, K, vec); }
+    __device__ __forceinline__ Raw zero() const { return make_float4(0.f, 0.f, 0.f, 0.f); }
+    __device__ __forceinline__ float4 value4(const Raw& r, float) const { return r; }
 };
 
 struct TcSmem {
@@ -198,20 +201,26 @@ k_gemm_tc(Prod prod, const uint32_t* __restrict__ Bimg, const float* __restrict_
     // 16-byte group lane%8), so one 16-byte load per operand and one 16-byte shared store per hi / lo image
     // cover four elements — the staging loop was instruction-issue bound with one element per load and store
     // (ncu r1g: issue slots 50 % busy, tensor pipe 7 %).
-    TcRaw4 pre[4];
+    // Prod::PD sets of raw operands live in registers: with PD = 2 the loads of chunk it+2 are issued while chunk it's
+    // MMAs run, so a whole iteration passes before they are consumed (with one set the load latency sat on the
+    // critical path of every iteration — ncu r1i: 35 % of the issue slots used, tensor pipe 12-31 %).
+    constexpr int PD = Prod::PD;
+    typename Prod::Raw pre[PD][4];
     const int st_row = warp * 16 + (lane >> 3), st_k4 = lane & 7;
-    auto prefetch = [&](int tile_idx, int kc) {
-        const int k = kc * TC_BK + st_k4 * 4;
-        const int b = tile_idx & 1;
+    auto prefetch = [&](auto set_c, int tile_i, int kc_i) {
+        constexpr int SET = decltype(set_c)::value;
+        const int k = kc_i * TC_BK + st_k4 * 4;
+        const int b = tile_i & 1;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int64_t o0 = meta0[b][st_row + 4 * i];
-            if (o0 >= 0 && k < K) pre[i] = prod.raw4(o0, meta1[b][st_row + 4 * i], k, K);
-            else pre[i] = TcRaw4{make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
+            if (o0 >= 0 && k < K) pre[SET][i] = prod.raw4(o0, meta1[b][st_row + 4 * i], k, K);
+            else pre[SET][i] = prod.zero();
         }
     };
-    const uint32_t total = (uint32_t)my_tiles * (uint32_t)kchunks;
-    if (total) prefetch(0, 0);
+    const uint32_t total = (uint32_t)my_tiles * (uint32_t)kchunks;   // kchunks ≥ 2 (the launcher pads): chunk it+2 is in this or the next tile
+    if (total) prefetch(std::integral_constant<int, 0>{}, 0, 0);
+    if (PD == 2 && total > 1) prefetch(std::integral_constant<int, PD - 1>{}, 0, 1);
     // B chunk of iteration `it` → stage it&1, issued ONE iteration ahead (right after the MMAs of it-1 are
     // queued) so that the bulk copy's latency hides behind those MMAs and the next A staging
     auto issue_b = [&](uint32_t it, int kc_b) {
@@ -225,7 +234,8 @@ k_gemm_tc(Prod prod, const uint32_t* __restrict__ Bimg, const float* __restrict_
     if (total && tid == 0) issue_b(0, 0);
 
     int tile_idx = 0, kc = 0;
-    for (uint32_t it = 0; it < total; ++it) {
+    auto step = [&](auto par_c, uint32_t it) {
+        constexpr int SET = PD == 2 ? decltype(par_c)::value : 0;      // register set holding chunk `it`
         const int s = it & 1;
         const uint32_t use = it >> 1;
         uint8_t* st = smem + (size_t)s * STAGE;
@@ -238,12 +248,12 @@ k_gemm_tc(Prod prod, const uint32_t* __restrict__ Bimg, const float* __restrict_
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int r = st_row + 4 * i;
-                const float a = meta2[b][r];
+                const float4 v = prod.value4(pre[SET][i], meta2[b][r]);
                 uint4 hi, lo;
-                split_tf32_fast(prod.value(pre[i].x.x, pre[i].y.x, a), hi.x, lo.x);
-                split_tf32_fast(prod.value(pre[i].x.y, pre[i].y.y, a), hi.y, lo.y);
-                split_tf32_fast(prod.value(pre[i].x.z, pre[i].y.z, a), hi.z, lo.z);
-                split_tf32_fast(prod.value(pre[i].x.w, pre[i].y.w, a), hi.w, lo.w);
+                split_tf32_fast(v.x, hi.x, lo.x);
+                split_tf32_fast(v.y, hi.y, lo.y);
+                split_tf32_fast(v.z, hi.z, lo.z);
+                split_tf32_fast(v.w, hi.w, lo.w);
                 const uint32_t off = sw128_offset(r, st_k4 * 4);      // one whole 16-byte group of the swizzled row
                 *reinterpret_cast<uint4*>(a_hi + off) = hi;
                 *reinterpret_cast<uint4*>(a_lo + off) = lo;
@@ -275,7 +285,11 @@ k_gemm_tc(Prod prod, const uint32_t* __restrict__ Bimg, const float* __restrict_
             if (use1 > 0) mbar_wait(&mma_bar[s ^ 1], (use1 - 1) & 1);
             issue_b(it + 1, tile_end ? 0 : kc + 1);
         }
-        if (it + 1 < total) prefetch(tile_end ? tile_idx + 1 : tile_idx, tile_end ? 0 : kc + 1);
+        if (it + PD < total) {                               // chunk it+PD → the register set chunk `it` just left
+            int t2 = tile_idx, k2 = kc + PD;
+            if (k2 >= kchunks) { k2 -= kchunks; ++t2; }
+            prefetch(std::integral_constant<int, SET>{}, t2, k2);
+        }
         if (tile_end) {
             // ---- epilogue: the last commit covers every MMA of the tile
             mbar_wait(&mma_bar[s], use & 1);
@@ -357,6 +371,10 @@ k_gemm_tc(Prod prod, const uint32_t* __restrict__ Bimg, const float* __restrict_
         } else {
             ++kc;
         }
+    };
+    for (uint32_t it = 0; it < total; it += 2) {            // unrolled by two: the register set of a chunk is static
+        step(std::integral_constant<int, 0>{}, it);
+        if (it + 1 < total) step(std::integral_constant<int, 1>{}, it + 1);
     }
     if (warp == 0) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
@@ -368,6 +386,7 @@ template <int NT, int MINB, class Prod, int EPI = TC_EPI_STORE>
 static int launch_tc(const Prod& prod, const uint32_t* img, const float* bias, int relu, float* C, int64_t ldc, int32_t M,
                      int32_t N, int32_t K, int32_t n_pad, int32_t kchunks, cudaStream_t s, uint32_t* sign_words = nullptr,
                      int32_t words_per_row = 0, uint32_t* minabs_bits = nullptr) {
+    if (kchunks < 2) { set_error("launch_tc: kchunks must be >= 2 (tc_kchunks pads)"); return LT_ERR_INTERNAL; }
     const size_t smem = tc_smem_bytes<NT>();
     LT_CUDA(cudaFuncSetAttribute(k_gemm_tc<NT, MINB, Prod, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int tiles_m = (M + TC_BM - 1) / TC_BM;
@@ -380,6 +399,10 @@ static int launch_tc(const Prod& prod, const uint32_t* img, const float* bias, i
     LT_LAUNCH_CHECK();
     return LT_OK;
 }
+
+// K chunks of a product: at least two, so that the kernel's two-chunk look-ahead never leaves the next tile
+// (a padded chunk lies past K: its A and B are zeros and none of its K steps is issued)
+static inline int32_t tc_kchunks(int32_t K) { const int32_t c = (K + TC_BK - 1) / TC_BK; return c < 2 ? 2 : c; }
 
 // N tile used for an output width (a few instantiated widths only) and the padded width
 static inline int tc_pick_nt(int N) {
