@@ -137,6 +137,9 @@ __device__ __forceinline__ int64_t upper_bound(const T* __restrict__ a, int64_t 
     return lo;
 }
 
+// non-zeros per warp work item of the CSR SpMM (spmm.cu); the attack plan sizes the segment list with it
+constexpr int SPMM_SEG = 256;
+
 // ---- primitives implemented in scan.cu / radix_sort.cu ----
 // out has n+1 entries: out[0] = 0, out[k] = sum(in[0..k)), out[n] = total.  in may alias out.
 int exclusive_scan_i32(const int32_t* in, int32_t* out, int64_t n, cudaStream_t s);

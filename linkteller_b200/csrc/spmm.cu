@@ -12,7 +12,6 @@
 
 namespace lt {
 
-constexpr int SPMM_SEG = 256;      // non-zeros per warp work item
 constexpr int SPMM_THREADS = 256;  // 8 warps per CTA
 
 // Row lists.  A product runs over list positions t = 0..n_list-1; position t stands for output row
@@ -386,9 +385,22 @@ k_spmm_scalar(const int32_t* __restrict__ indptr, const int32_t* __restrict__ in
     }
 }
 
+// seg_off_known / total_seg_known (optional): exclusive scan of the per-row segment counts (n_rows+1 entries,
+// SPMM_SEG non-zeros per segment, at least one per row) and its total, when the caller already has them — the
+// attack plan does — so that the product needs neither the counting pass nor its host synchronisation.
+int spmm_csr_f32_seg(const int32_t* indptr, const int32_t* indices, const float* values, int32_t n_cols,
+                     const int32_t* rows, int32_t n_rows, const float* B, int64_t ldb, int32_t d, const float* bias, int relu,
+                     float* C, int64_t ldc, const int32_t* seg_off_known, int64_t total_seg_known, cudaStream_t s);
+
 int spmm_csr_f32(const int32_t* indptr, const int32_t* indices, const float* values, int32_t n_cols,
                  const int32_t* rows, int32_t n_rows, const float* B, int64_t ldb, int32_t d, const float* bias, int relu,
                  float* C, int64_t ldc, cudaStream_t s) {
+    return spmm_csr_f32_seg(indptr, indices, values, n_cols, rows, n_rows, B, ldb, d, bias, relu, C, ldc, nullptr, -1, s);
+}
+
+int spmm_csr_f32_seg(const int32_t* indptr, const int32_t* indices, const float* values, int32_t n_cols,
+                     const int32_t* rows, int32_t n_rows, const float* B, int64_t ldb, int32_t d, const float* bias, int relu,
+                     float* C, int64_t ldc, const int32_t* seg_off_known, int64_t total_seg_known, cudaStream_t s) {
     if (n_rows == 0 || d == 0) return LT_OK;
     const bool vec = (d % 4 == 0) && (ldb % 4 == 0) && (ldc % 4 == 0) && d <= 512 && (int64_t)n_cols * (ldb / 4) < ((int64_t)1 << 32) &&
                      ((uintptr_t)B % 16 == 0) && ((uintptr_t)C % 16 == 0) && (!bias || (uintptr_t)bias % 16 == 0);
@@ -410,7 +422,8 @@ int spmm_csr_f32(const int32_t* indptr, const int32_t* indices, const float* val
     Scratch scratch(s);
 
     // the plain pass over a row list (sel == null: the whole list); total_seg < 0: not known yet (one 4-byte sync)
-    auto plain_pass = [&](const int32_t* sel, int32_t n_list, int32_t* seg_off, int64_t total_seg) -> int {
+    auto plain_pass = [&](const int32_t* sel, int32_t n_list, const int32_t* seg_off_in, int64_t total_seg) -> int {
+        int32_t* seg_off = const_cast<int32_t*>(seg_off_in);   // written only when the counts are not known yet
         if (n_list == 0) return LT_OK;
         if (total_seg < 0) {
             k_spmm_segcount<<<(unsigned)ceil_div(n_list, 256), 256, 0, s>>>(indptr, rows, sel, nullptr, n_list, SPMM_SEG, seg_off);
@@ -452,6 +465,7 @@ int spmm_csr_f32(const int32_t* indptr, const int32_t* indices, const float* val
     const int32_t lmin = pl ? atoi(pl) : 64;
     const bool use_panel = d4 <= 32 && b_bytes >= ((int64_t)256 << 20) && n_rows >= 32768 && getenv("LT_SPMM_PANEL");
     if (!use_panel) {
+        if (seg_off_known && total_seg_known >= 0) return plain_pass(nullptr, n_rows, seg_off_known, total_seg_known);
         int32_t* seg_off;
         LT_TRY(scratch.alloc(&seg_off, (size_t)n_rows + 1));
         return plain_pass(nullptr, n_rows, seg_off, -1);
