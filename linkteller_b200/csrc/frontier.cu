@@ -17,7 +17,7 @@
 //   F1 k_frontier_dq     : ΔQ[e,:] for every incidence      (reads one H row per incidence: HBM-bound
 //                          on large graphs; a [64 x h]·[h x c] register-blocked product per CTA)
 //   F2 k_frontier_reduce : out[j,i] = ‖Σ_k w_k·ΔQ[e_k,:]‖₂  (segmented, deterministic)
-#include "gemm_tc.cuh"
+#include "gemm_ws.cuh"
 
 #include <stdlib.h>
 
@@ -733,6 +733,15 @@ static int frontier_dq(const lt_plan* p, const int32_t* h_index, const float* H,
         LT_TRY(scratch.alloc(&img, (size_t)kchunks * 2 * n_pad * TC_BK));
         LT_TRY(tc_prepack_b(W2, c, 0, c, h, n_pad, img, s));
         const DeltaRProd prod{p->s_j, h_index, p->s_a, p_index, H, ldh, P, ldp, delta, inv_delta};
+        if (tc_use_ws()) {
+            switch (nt) {
+                case 32: return launch_ws<32>(prod, img, nullptr, 0, dq, lddq, (int32_t)E, c, h, n_pad, kchunks, s);
+                case 48: return launch_ws<48>(prod, img, nullptr, 0, dq, lddq, (int32_t)E, c, h, n_pad, kchunks, s);
+                case 64: return launch_ws<64>(prod, img, nullptr, 0, dq, lddq, (int32_t)E, c, h, n_pad, kchunks, s);
+                case 128: return launch_ws<128>(prod, img, nullptr, 0, dq, lddq, (int32_t)E, c, h, n_pad, kchunks, s);
+                default: return launch_ws<256>(prod, img, nullptr, 0, dq, lddq, (int32_t)E, c, h, n_pad, kchunks, s);
+            }
+        }
         switch (nt) {
             case 32: LT_TRY((launch_tc<32, 2>(prod, img, nullptr, 0, dq, lddq, (int32_t)E, c, h, n_pad, kchunks, s))); break;
             case 48: LT_TRY((launch_tc<48, 2>(prod, img, nullptr, 0, dq, lddq, (int32_t)E, c, h, n_pad, kchunks, s))); break;
@@ -788,6 +797,15 @@ static int frontier_dq_signs(const lt_plan* p, const uint32_t* sign_words, int32
     k_slow_mark<<<(unsigned)ceil_div(E, 256), 256, 0, s>>>(p->s_j, p->s_rho, p->s_a, E, minabs_bits, pmax, delta, slow_list, n_fixed);
     LT_LAUNCH_CHECK();
     const MaskProd prod{p->s_j, p->s_rho, p->s_a, p_index, sign_words, wpr, P, ldp};
+    if (tc_use_ws()) {
+        switch (nt) {
+            case 32: LT_TRY((launch_ws<32>(prod, img, nullptr, 0, dq, lddq, (int32_t)E, c, h, n_pad, kchunks, s))); break;
+            case 48: LT_TRY((launch_ws<48>(prod, img, nullptr, 0, dq, lddq, (int32_t)E, c, h, n_pad, kchunks, s))); break;
+            case 64: LT_TRY((launch_ws<64>(prod, img, nullptr, 0, dq, lddq, (int32_t)E, c, h, n_pad, kchunks, s))); break;
+            case 128: LT_TRY((launch_ws<128>(prod, img, nullptr, 0, dq, lddq, (int32_t)E, c, h, n_pad, kchunks, s))); break;
+            default: LT_TRY((launch_ws<256>(prod, img, nullptr, 0, dq, lddq, (int32_t)E, c, h, n_pad, kchunks, s))); break;
+        }
+    } else
     switch (nt) {
         case 32: LT_TRY((launch_tc<32, 2>(prod, img, nullptr, 0, dq, lddq, (int32_t)E, c, h, n_pad, kchunks, s))); break;
         case 48: LT_TRY((launch_tc<48, 2>(prod, img, nullptr, 0, dq, lddq, (int32_t)E, c, h, n_pad, kchunks, s))); break;

@@ -17,7 +17,9 @@
 //     commits them to the stage's mbarrier; two stages overlap staging with the MMAs;
 //   * epilogue: tcgen05.ld 32x32b (warp w reads TMEM lanes 32·(w%4)…, column half w/4), bias / ReLU,
 //     16-byte stores of the row.
-#include "gemm_tc.cuh"
+#include "gemm_ws.cuh"
+
+#include <stdlib.h>
 
 namespace lt {
 
@@ -51,6 +53,13 @@ int tc_prepack_b(const float* B, int64_t ldb, int transB, int32_t N, int32_t K, 
     return LT_OK;
 }
 
+// LT_TC_WS=0 selects the lock-step kernel (k_gemm_tc) instead of the warp-specialised one (k_gemm_ws)
+bool tc_use_ws() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("LT_TC_WS"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v == 1;
+}
+
 // handled = false ⇒ the caller uses the fp32 SIMT kernel (tiny problems are not worth a tensor-core launch)
 int gemm_3xtf32(const float* A, int64_t lda, const int32_t* a_rows, const float* B, int64_t ldb, int transB,
                 const float* bias, int relu, float* C, int64_t ldc, int32_t M, int32_t N, int32_t K, cudaStream_t s,
@@ -66,6 +75,17 @@ int gemm_3xtf32(const float* A, int64_t lda, const int32_t* a_rows, const float*
     LT_TRY(scratch.alloc(&img, (size_t)kchunks * 2 * n_pad * TC_BK));
     LT_TRY(tc_prepack_b(B, ldb, transB, N, K, n_pad, img, s));
     const PlainA prod{A, lda, a_rows};
+    if (tc_use_ws()) {
+        switch (nt) {
+            case 32: LT_TRY((launch_ws<32>(prod, img, bias, relu, C, ldc, M, N, K, n_pad, kchunks, s))); break;
+            case 48: LT_TRY((launch_ws<48>(prod, img, bias, relu, C, ldc, M, N, K, n_pad, kchunks, s))); break;
+            case 64: LT_TRY((launch_ws<64>(prod, img, bias, relu, C, ldc, M, N, K, n_pad, kchunks, s))); break;
+            case 128: LT_TRY((launch_ws<128>(prod, img, bias, relu, C, ldc, M, N, K, n_pad, kchunks, s))); break;
+            default: LT_TRY((launch_ws<256>(prod, img, bias, relu, C, ldc, M, N, K, n_pad, kchunks, s))); break;
+        }
+        *handled = true;
+        return LT_OK;
+    }
     switch (nt) {
         case 32: LT_TRY((launch_tc<32, 2>(prod, img, bias, relu, C, ldc, M, N, K, n_pad, kchunks, s))); break;
         case 48: LT_TRY((launch_tc<48, 2>(prod, img, bias, relu, C, ldc, M, N, K, n_pad, kchunks, s))); break;
@@ -91,6 +111,14 @@ int gemm_3xtf32_signs(const float* A, int64_t lda, const float* B, int64_t ldb, 
     LT_TRY(scratch.alloc(&img, (size_t)kchunks * 2 * n_pad * TC_BK));
     LT_TRY(tc_prepack_b(B, ldb, 0, N, K, n_pad, img, s));
     const PlainA prod{A, lda, nullptr};
+    if (tc_use_ws()) {
+        switch (nt) {
+            case 32: return launch_ws<32, PlainA, TC_EPI_SIGN>(prod, img, bias, 0, nullptr, 0, M, N, K, n_pad, kchunks, s, sign_words, wpr, minabs_bits);
+            case 64: return launch_ws<64, PlainA, TC_EPI_SIGN>(prod, img, bias, 0, nullptr, 0, M, N, K, n_pad, kchunks, s, sign_words, wpr, minabs_bits);
+            case 128: return launch_ws<128, PlainA, TC_EPI_SIGN>(prod, img, bias, 0, nullptr, 0, M, N, K, n_pad, kchunks, s, sign_words, wpr, minabs_bits);
+            default: return launch_ws<256, PlainA, TC_EPI_SIGN>(prod, img, bias, 0, nullptr, 0, M, N, K, n_pad, kchunks, s, sign_words, wpr, minabs_bits);
+        }
+    }
     switch (nt) {
         case 32: LT_TRY((launch_tc<32, 2, PlainA, TC_EPI_SIGN>(prod, img, bias, 0, nullptr, 0, M, N, K, n_pad, kchunks, s, sign_words, wpr, minabs_bits))); break;
         case 64: LT_TRY((launch_tc<64, 2, PlainA, TC_EPI_SIGN>(prod, img, bias, 0, nullptr, 0, M, N, K, n_pad, kchunks, s, sign_words, wpr, minabs_bits))); break;
