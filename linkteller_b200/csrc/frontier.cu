@@ -116,6 +116,30 @@ __global__ void k_compact_rows(const int32_t* __restrict__ flag, const int32_t* 
     }
 }
 
+// Σ over the marked rows of their SpMM segment counts and of their lengths (grid-stride, one atomic pair per CTA):
+// known before the first host sync, the restricted SpMM can be launched as soon as the rows are compacted.
+__global__ void __launch_bounds__(256)
+k_seg_total(const int32_t* __restrict__ flag, const int32_t* __restrict__ indptr, int32_t n, unsigned long long* __restrict__ tot) {
+    unsigned long long seg = 0, nnz = 0;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x)
+        if (flag[r]) {
+            const int32_t len = indptr[r + 1] - indptr[r];
+            seg += len <= SPMM_SEG ? 1 : (len + SPMM_SEG - 1) / SPMM_SEG;
+            nnz += len;
+        }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { seg += __shfl_xor_sync(LT_FULL, seg, o); nnz += __shfl_xor_sync(LT_FULL, nnz, o); }
+    __shared__ unsigned long long sh[2][8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { sh[0][warp] = seg; sh[1][warp] = nnz; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) { seg += sh[0][w]; nnz += sh[1][w]; }
+        atomicAdd(&tot[0], seg);
+        atomicAdd(&tot[1], nnz);
+    }
+}
+
 // one thread per incidence e: owner row j (binary search in s_indptr), frontier row r, and
 // a_e = Â[r,v] looked up in row r (the value the reference's spmm multiplies P'[v] with; a missing
 // entry means Â's pattern is not symmetric).  Thread-per-incidence keeps hub test nodes from
@@ -574,10 +598,43 @@ static int plan_alloc(lt_plan* p, T** out, size_t count, cudaStream_t s) {
     return plan_own(p, q);
 }
 
+// A high-priority side stream per device (created once): the second half of the plan runs on it while the restricted
+// SpMM — which only needs the compacted frontier rows — already occupies the caller's stream.
+static cudaStream_t side_stream() {
+    static cudaStream_t streams[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    if (!streams[dev]) {
+        int lo_p = 0, hi_p = 0;
+        cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p);
+        if (cudaStreamCreateWithPriority(&streams[dev], cudaStreamNonBlocking, hi_p) != cudaSuccess) streams[dev] = nullptr;
+    }
+    return streams[dev];
+}
+
+// joins the side stream back into the caller's stream on every exit path of plan_build
+struct StreamJoin {
+    cudaStream_t main, side;
+    cudaEvent_t ev = nullptr;
+    StreamJoin(cudaStream_t m, cudaStream_t sd) : main(m), side(sd) {}
+    ~StreamJoin() {
+        if (side == main) return;
+        if (!ev) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+        cudaEventRecord(ev, side);
+        cudaStreamWaitEvent(main, ev, 0);
+        cudaEventDestroy(ev);
+    }
+};
+
+// `early` (nullable) is called once the frontier rows, their SpMM segment offsets and the sizes R / E / total_seg are
+// known: the caller enqueues the restricted precompute on `s` there, and the rest of the plan moves to the side stream.
+typedef int (*plan_early_fn)(lt_plan* p, void* ctx);
+
 static int plan_build(lt_plan* p, const int32_t* indptr, const int32_t* indices, const float* values,
-                      const int32_t* test_nodes, cudaStream_t s) {
+                      const int32_t* test_nodes, cudaStream_t s, plan_early_fn early = nullptr, void* early_ctx = nullptr) {
     const int32_t n = p->n, T = p->T, lo = p->lo, Ts = p->Ts;
     Scratch scratch(s);
+    struct ScopeBox { ProfScope* p; ~ScopeBox() { delete p; } void end() { delete p; p = nullptr; } } prof_a{new ProfScope("plan", s)};
     int32_t *tmap, *rmap, *flag, *all_len, *rlen;
     int* err;
     int64_t* sums;  // [0]=Σ all_len  [1]=Σ rlen
@@ -603,7 +660,14 @@ static int plan_build(lt_plan* p, const int32_t* indptr, const int32_t* indices,
     int32_t* pos;
     LT_TRY(scratch.alloc(&pos, (size_t)n + 1));
     LT_TRY(exclusive_scan_i32(flag, pos, n, s));
+    unsigned long long* seg_tot;
+    unsigned long long h_seg_tot[2] = {0, 0};
+    LT_TRY(scratch.alloc(&seg_tot, 2));
+    LT_CUDA(cudaMemsetAsync(seg_tot, 0, 16, s));
+    k_seg_total<<<(unsigned)num_sms() * 2, 256, 0, s>>>(flag, indptr, n, seg_tot);
+    LT_LAUNCH_CHECK();
     int32_t h3[3];
+    LT_CUDA(cudaMemcpyAsync(h_seg_tot, seg_tot, 16, cudaMemcpyDeviceToHost, s));
     LT_CUDA(cudaMemcpyAsync(&h3[0], p->s_indptr + Ts, 4, cudaMemcpyDeviceToHost, s));
     LT_CUDA(cudaMemcpyAsync(&h3[1], pos + n, 4, cudaMemcpyDeviceToHost, s));
     LT_CUDA(cudaMemcpyAsync(&h3[2], all_len + T, 4, cudaMemcpyDeviceToHost, s));
@@ -622,6 +686,30 @@ static int plan_build(lt_plan* p, const int32_t* indptr, const int32_t* indices,
     LT_TRY(plan_alloc(p, &p->seg_off, (size_t)R + 1, s));
     k_compact_rows<<<(unsigned)ceil_div(n, 256), 256, 0, s>>>(flag, pos, n, indptr, rmap, p->rows, rlen, p->seg_off);
     LT_LAUNCH_CHECK();
+    LT_TRY(exclusive_scan_i32(p->seg_off, p->seg_off, R, s));
+    p->total_seg = (int64_t)h_seg_tot[0];
+    p->nnzR = (int64_t)h_seg_tot[1];
+
+    // ---- fork: the caller's precompute goes onto `s` now, the rest of the plan onto the side stream
+    cudaStream_t s2 = s;
+    if (early) {
+        cudaStream_t sd = side_stream();
+        if (sd) {
+            cudaEvent_t ev;
+            LT_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            cudaError_t e1 = cudaEventRecord(ev, s);
+            cudaError_t e2 = e1 == cudaSuccess ? cudaStreamWaitEvent(sd, ev, 0) : e1;
+            cudaEventDestroy(ev);
+            if (e2 != cudaSuccess) { set_error("plan: fork onto the side stream failed: %s", cudaGetErrorString(e2)); return LT_ERR_CUDA; }
+            s2 = sd;
+        }
+    }
+    StreamJoin join(s, s2);                     // declared before scratch2: the join runs after scratch2's frees are queued
+    prof_a.end();
+    if (early) LT_TRY(early(p, early_ctx));
+    s = s2;                                     // everything below runs on the side stream (or still on the caller's)
+    Scratch scratch2(s);
+    ProfScope prof_b(s2 != join.main ? "plan_side" : "plan", s);
     LT_TRY(plan_alloc(p, &p->s_j, (size_t)E, s));
     LT_TRY(plan_alloc(p, &p->s_rho, (size_t)E, s));
     LT_TRY(plan_alloc(p, &p->s_a, (size_t)E, s));
@@ -634,7 +722,7 @@ static int plan_build(lt_plan* p, const int32_t* indptr, const int32_t* indices,
     // observers
     int32_t* cursor;
     LT_TRY(plan_alloc(p, &p->b_indptr, (size_t)R + 1, s));
-    LT_TRY(scratch.alloc(&cursor, (size_t)R + 1));
+    LT_TRY(scratch2.alloc(&cursor, (size_t)R + 1));
     LT_TRY(plan_alloc(p, &p->b_i, (size_t)nb_cap, s));
     LT_TRY(plan_alloc(p, &p->b_w, (size_t)nb_cap, s));
     LT_CUDA(cudaMemsetAsync(p->b_indptr, 0, ((size_t)R + 1) * 4, s));
@@ -649,21 +737,17 @@ static int plan_build(lt_plan* p, const int32_t* indptr, const int32_t* indices,
     // records
     int32_t* rc;
     int64_t* rec_off;
-    LT_TRY(scratch.alloc(&rc, (size_t)E + 1));
-    LT_TRY(scratch.alloc(&rec_off, (size_t)E + 1));
+    LT_TRY(scratch2.alloc(&rc, (size_t)E + 1));
+    LT_TRY(scratch2.alloc(&rec_off, (size_t)E + 1));
     if (E) {
         k_rec_counts<<<(unsigned)ceil_div(E, 256), 256, 0, s>>>(p->s_rho, E, p->b_indptr, rc);
         LT_LAUNCH_CHECK();
     }
     LT_TRY(exclusive_scan_i32_to_i64(rc, rec_off, E, s));
-    LT_TRY(exclusive_scan_i32(rlen, rlen, R, s));   // Σ nnz of frontier rows (for the byte accounting)
-    LT_TRY(exclusive_scan_i32(p->seg_off, p->seg_off, R, s));
     int64_t hM = 0;
-    int32_t hNB = 0, hnnzR = 0, hseg = 0;
-    LT_CUDA(cudaMemcpyAsync(&hseg, p->seg_off + R, 4, cudaMemcpyDeviceToHost, s));
+    int32_t hNB = 0;
     LT_CUDA(cudaMemcpyAsync(&hM, rec_off + E, 8, cudaMemcpyDeviceToHost, s));
     LT_CUDA(cudaMemcpyAsync(&hNB, p->b_indptr + R, 4, cudaMemcpyDeviceToHost, s));
-    LT_CUDA(cudaMemcpyAsync(&hnnzR, rlen + R, 4, cudaMemcpyDeviceToHost, s));
     LT_CUDA(cudaMemcpyAsync(&herr, err, sizeof(int), cudaMemcpyDeviceToHost, s));
     LT_CUDA(cudaStreamSynchronize(s));
     if (herr & 4) {
@@ -672,8 +756,6 @@ static int plan_build(lt_plan* p, const int32_t* indptr, const int32_t* indices,
     }
     p->M = hM;
     p->NB = hNB;
-    p->nnzR = hnnzR;
-    p->total_seg = hseg;
     if (hM >= ((int64_t)1 << 31)) { set_error("lt_plan_create: %lld records exceed 2^31", (long long)hM); return LT_ERR_CAPACITY; }
     const int64_t M = hM;
     LT_TRY(plan_alloc(p, &p->rec_key, (size_t)M, s));
@@ -691,7 +773,7 @@ static int plan_build(lt_plan* p, const int32_t* indptr, const int32_t* indices,
         BitRange ranges[2] = {{0, bits_for((uint64_t)(T - 1))}, {32, 32 + bits_for((uint64_t)(Ts > 1 ? Ts - 1 : 1))}};
         LT_TRY(radix_sort_u64(p->rec_key, p->rec_val, M, ranges, Ts > 1 ? 2 : 1, s));
         int32_t* head;
-        LT_TRY(scratch.alloc(&head, (size_t)M + 1));
+        LT_TRY(scratch2.alloc(&head, (size_t)M + 1));
         k_rec_heads<<<(unsigned)ceil_div(M, 256), 256, 0, s>>>(p->rec_key, M, head);
         LT_LAUNCH_CHECK();
         LT_TRY(exclusive_scan_i32(head, head, M, s));
@@ -1204,11 +1286,7 @@ extern "C" int lt_plan_create(const int32_t* indptr, const int32_t* indices, con
     cudaStream_t s = (cudaStream_t)stream;
     lt_plan* p = new lt_plan();
     p->n = n; p->T = T; p->lo = lo; p->hi = hi; p->Ts = hi - lo;
-    int st;
-    {
-        ProfScope prof("plan", s);
-        st = plan_build(p, indptr, indices, values, test_nodes, s);
-    }
+    const int st = plan_build(p, indptr, indices, values, test_nodes, s);
     if (st != LT_OK) { lt_plan_destroy(p, stream); return st; }
     *plan_host = p;
     return LT_OK;
@@ -1251,111 +1329,124 @@ extern "C" int lt_influence_rows(const lt_plan* plan, const float* H_R, int64_t 
     return influence_rows(plan, H_R, ldh, P, ldp, p_index, W2, h, c, delta, out, ldo, (cudaStream_t)stream);
 }
 
-// plan + restricted precompute + frontier in one call (the whole timed hot path of one rank)
+// plan + restricted precompute + frontier in one call (the whole timed hot path of one rank).
+// The restricted precompute only needs the compacted frontier rows, so it is enqueued on the caller's stream from the
+// plan's `early` hook while the second half of the plan (incidences, observers, records, sort) runs on the side stream.
+namespace {
+struct AttackCtx {
+    const int32_t *indptr, *indices; const float* values; int32_t n;
+    const float* X; int64_t ldx; int32_t f;
+    const float *W1, *b1; int32_t h, c;
+    const int32_t* test_nodes; int32_t lo;
+    cudaStream_t s; Scratch* scratch;
+    // produced by the hook
+    bool sign_path = false;
+    float *Pt = nullptr, *HR = nullptr, *AX = nullptr;
+    uint32_t *signs = nullptr, *minabs = nullptr;
+    int32_t* n_fixed = nullptr;
+    int32_t wpr = 0;
+};
+
+int attack_early(lt_plan* plan, void* vctx) {
+    AttackCtx& a = *static_cast<AttackCtx*>(vctx);
+    cudaStream_t s = a.s;
+    Scratch& scratch = *a.scratch;
+    const int32_t R = plan->R, Ts = plan->Ts, n = a.n, f = a.f, h = a.h, c = a.c;
+    LT_TRY(scratch.alloc(&a.Pt, (size_t)Ts * h));
+    {   // P_v = X[v]·W1 for the slice (gathered rows)
+        ProfScope prof("gemm_pv", s);
+        LT_TRY(gemm_f32(a.X, a.ldx, a.test_nodes + a.lo, a.W1, h, 0, nullptr, 0, a.Pt, h, Ts, h, f, 0, s));
+    }
+    const bool aggregate_first = (f < h) && (f % 4 == 0) && (a.ldx % 4 == 0) && ((uintptr_t)a.X % 16 == 0);
+    // sign-mask path: H_R is never written — the GEMM keeps one bit per element and the row's smallest magnitude
+    // (36 bytes per frontier row instead of 4h), F1 reads those, and the rows where a ReLU can switch are patched
+    a.sign_path = aggregate_first && frontier_use_tc(plan->E, h, c) && h >= 16 && (int64_t)R * h * f >= ((int64_t)1 << 24) &&
+                  (uintptr_t)a.W1 % 16 == 0 && !getenv("LT_NO_SIGN_PATH");
+    if (aggregate_first) {
+        // H_R = (Â[R,:]·X)·W1 + b1 : gathers f floats per non-zero instead of h
+        LT_TRY(scratch.alloc(&a.AX, (size_t)R * f));
+        {
+            ProfScope prof("spmm_ax", s);
+            LT_TRY(spmm_csr_f32_seg(a.indptr, a.indices, a.values, n, plan->rows, R, a.X, a.ldx, f, nullptr, 0, a.AX, f,
+                                    plan->seg_off, plan->total_seg, s));
+        }
+        ProfScope prof("gemm_h", s);
+        if (a.sign_path) {
+            a.wpr = (h + 31) / 32;
+            LT_TRY(scratch.alloc(&a.signs, (size_t)R * a.wpr));
+            LT_TRY(scratch.alloc(&a.minabs, (size_t)R));
+            LT_TRY(scratch.alloc(&a.n_fixed, 1));
+            LT_CUDA(cudaMemsetAsync(a.minabs, 0x7f, (size_t)R * 4, s));
+            LT_CUDA(cudaMemsetAsync(a.n_fixed, 0, 4, s));
+            LT_TRY(gemm_3xtf32_signs(a.AX, f, a.W1, h, a.b1, R, h, f, a.signs, a.minabs, s));
+        } else {
+            LT_TRY(scratch.alloc(&a.HR, (size_t)R * h));
+            LT_TRY(gemm_f32(a.AX, f, nullptr, a.W1, h, 0, a.b1, 0, a.HR, h, R, h, f, 0, s));
+        }
+    } else {
+        // H_R = Â[R,:]·(X·W1) + b1
+        float* Pfull = nullptr;
+        LT_TRY(scratch.alloc(&Pfull, (size_t)n * h));
+        LT_TRY(scratch.alloc(&a.HR, (size_t)R * h));
+        {
+            ProfScope prof("gemm_p", s);
+            LT_TRY(gemm_f32(a.X, a.ldx, nullptr, a.W1, h, 0, nullptr, 0, Pfull, h, n, h, f, 0, s));
+        }
+        ProfScope prof("spmm_h", s);
+        LT_TRY(spmm_csr_f32_seg(a.indptr, a.indices, a.values, n, plan->rows, R, Pfull, h, h, a.b1, 0, a.HR, h, plan->seg_off,
+                                plan->total_seg, s));
+    }
+    return LT_OK;
+}
+}  // namespace
+
 extern "C" int lt_attack_efficient(const int32_t* indptr, const int32_t* indices, const float* values, int32_t n,
                                    const float* X, int64_t ldx, int32_t f, const float* W1, const float* b1,
                                    const float* W2, int32_t h, int32_t c, const int32_t* test_nodes, int32_t T,
                                    int32_t lo, int32_t hi, float delta, float* out, int64_t ldo, int64_t* info_host,
                                    lt_stream_t stream) {
+    LT_CHECK_ARG(indptr && indices && values && test_nodes, "lt_attack_efficient: null pointer");
     LT_CHECK_ARG(X && W1 && b1 && W2 && out, "lt_attack_efficient: null pointer");
     LT_CHECK_ARG(f > 0 && h > 0 && c > 0 && ldx >= f && h % 4 == 0, "lt_attack_efficient: sizes (h % 4 == 0)");
+    LT_CHECK_ARG(n > 0 && T > 0 && lo >= 0 && hi >= lo && hi <= T, "lt_attack_efficient: need 0 <= lo <= hi <= T");
     cudaStream_t s = (cudaStream_t)stream;
     if (hi == lo) return LT_OK;
-    lt_plan* plan = nullptr;
-    LT_TRY(lt_plan_create(indptr, indices, values, n, test_nodes, T, lo, hi, stream, &plan));
-    int st = LT_OK;
+    lt_plan* plan = new lt_plan();
+    plan->n = n; plan->T = T; plan->lo = lo; plan->hi = hi; plan->Ts = hi - lo;
+    int st;
     {
         Scratch scratch(s);
-        const int32_t R = plan->R, Ts = plan->Ts;
-        float *HR = nullptr, *Pt = nullptr;
-        st = scratch.alloc(&Pt, (size_t)Ts * h);
-        // P_v = X[v]·W1 for the slice (gathered rows)
+        AttackCtx a{indptr, indices, values, n, X, ldx, f, W1, b1, h, c, test_nodes, lo, s, &scratch};
+        st = plan_build(plan, indptr, indices, values, test_nodes, s, getenv("LT_NO_OVERLAP") ? nullptr : attack_early, &a);
+        if (st == LT_OK && getenv("LT_NO_OVERLAP")) st = attack_early(plan, &a);
         if (st == LT_OK) {
-            ProfScope prof("gemm_pv", s);
-            st = gemm_f32(X, ldx, test_nodes + lo, W1, h, 0, nullptr, 0, Pt, h, Ts, h, f, 0, s);
-        }
-        const bool aggregate_first = (f < h) && (f % 4 == 0) && (ldx % 4 == 0) && ((uintptr_t)X % 16 == 0);
-        // sign-mask path: H_R is never written — the GEMM keeps one bit per element and the row's smallest magnitude
-        // (36 bytes per frontier row instead of 4h), F1 reads those, and the rows where a ReLU can switch are patched
-        const bool sign_path = aggregate_first && frontier_use_tc(plan->E, h, c) && h >= 16 &&
-                               (int64_t)R * h * f >= ((int64_t)1 << 24) && plan->M > 0 && (uintptr_t)W1 % 16 == 0 &&
-                               !getenv("LT_NO_SIGN_PATH");
-        if (st == LT_OK && sign_path) {
-            float* AX = nullptr;
-            uint32_t *signs = nullptr, *minabs = nullptr;
-            float* dq = nullptr;
-            int32_t* n_fixed = nullptr;
-            const int32_t wpr = (h + 31) / 32;
-            const int32_t lddq = frontier_lddq(plan->E, h, c);
-            st = scratch.alloc(&AX, (size_t)R * f);
-            if (st == LT_OK) st = scratch.alloc(&signs, (size_t)R * wpr);
-            if (st == LT_OK) st = scratch.alloc(&minabs, (size_t)R);
-            if (st == LT_OK) st = scratch.alloc(&dq, (size_t)plan->E * lddq);
-            if (st == LT_OK) st = scratch.alloc(&n_fixed, 1);
-            if (st == LT_OK) {
-                ProfScope prof("spmm_ax", s);
-                st = spmm_csr_f32_seg(indptr, indices, values, n, plan->rows, R, X, ldx, f, nullptr, 0, AX, f, plan->seg_off,
-                                      plan->total_seg, s);
-            }
-            if (st == LT_OK) {
-                ProfScope prof("gemm_h", s);
-                if (cudaMemsetAsync(minabs, 0x7f, (size_t)R * 4, s) != cudaSuccess || cudaMemsetAsync(n_fixed, 0, 4, s) != cudaSuccess) {
-                    set_error("lt_attack_efficient: cudaMemsetAsync failed");
+            if (a.sign_path) {
+                const int32_t lddq = frontier_lddq(plan->E, h, c);
+                float* dq = nullptr;
+                if (cudaMemset2DAsync(out, (size_t)ldo * 4, 0, (size_t)T * 4, (size_t)plan->Ts, s) != cudaSuccess) {
+                    set_error("lt_attack_efficient: cudaMemset2DAsync failed");
                     st = LT_ERR_CUDA;
-                } else {
-                    st = gemm_3xtf32_signs(AX, f, W1, h, b1, R, h, f, signs, minabs, s);
                 }
-            }
-            if (st == LT_OK && cudaMemset2DAsync(out, (size_t)ldo * 4, 0, (size_t)T * 4, (size_t)Ts, s) != cudaSuccess) {
-                set_error("lt_attack_efficient: cudaMemset2DAsync failed");
-                st = LT_ERR_CUDA;
-            }
-            if (st == LT_OK)
-                st = frontier_dq_signs(plan, signs, wpr, minabs, AX, f, f, W1, b1, Pt, h, nullptr, W2, h, c, delta, dq, n_fixed, s);
-            if (st == LT_OK)
-                st = frontier_reduce(plan->rec_key, plan->rec_val, plan->grp_off, plan->n_groups, plan->big, plan->n_big, plan->M,
-                                     dq, lddq, c, out, ldo, s);
-            if (st == LT_OK && info_host) {
-                st = lt_plan_info(plan, h, c, info_host, stream);
-                int32_t nf = 0;
-                if (st == LT_OK && cudaMemcpyAsync(&nf, n_fixed, 4, cudaMemcpyDeviceToHost, s) == cudaSuccess &&
-                    cudaStreamSynchronize(s) == cudaSuccess)
-                    info_host[7] = nf;      // incidences that took the exact (recomputed) path
-            }
-        } else if (st == LT_OK) {
-            st = scratch.alloc(&HR, (size_t)R * h);
-        }
-        if (st == LT_OK && !sign_path) {
-            if (aggregate_first) {
-                // H_R = (Â[R,:]·X)·W1 + b1 : gathers f floats per non-zero instead of h
-                float* AX = nullptr;
-                st = scratch.alloc(&AX, (size_t)R * f);
-                if (st == LT_OK) {
-                    ProfScope prof("spmm_ax", s);
-                    st = spmm_csr_f32_seg(indptr, indices, values, n, plan->rows, R, X, ldx, f, nullptr, 0, AX, f, plan->seg_off,
-                                      plan->total_seg, s);
-                }
-                if (st == LT_OK) {
-                    ProfScope prof("gemm_h", s);
-                    st = gemm_f32(AX, f, nullptr, W1, h, 0, b1, 0, HR, h, R, h, f, 0, s);
+                if (st == LT_OK && plan->E > 0 && plan->M > 0) {
+                    st = scratch.alloc(&dq, (size_t)plan->E * lddq);
+                    if (st == LT_OK)
+                        st = frontier_dq_signs(plan, a.signs, a.wpr, a.minabs, a.AX, f, f, W1, b1, a.Pt, h, nullptr, W2, h, c, delta,
+                                               dq, a.n_fixed, s);
+                    if (st == LT_OK)
+                        st = frontier_reduce(plan->rec_key, plan->rec_val, plan->grp_off, plan->n_groups, plan->big, plan->n_big,
+                                             plan->M, dq, lddq, c, out, ldo, s);
                 }
             } else {
-                // H_R = Â[R,:]·(X·W1) + b1
-                float* Pfull = nullptr;
-                st = scratch.alloc(&Pfull, (size_t)n * h);
-                if (st == LT_OK) {
-                    ProfScope prof("gemm_p", s);
-                    st = gemm_f32(X, ldx, nullptr, W1, h, 0, nullptr, 0, Pfull, h, n, h, f, 0, s);
-                }
-                if (st == LT_OK) {
-                    ProfScope prof("spmm_h", s);
-                    st = spmm_csr_f32_seg(indptr, indices, values, n, plan->rows, R, Pfull, h, h, b1, 0, HR, h, plan->seg_off,
-                                          plan->total_seg, s);
-                }
+                st = influence_rows(plan, a.HR, h, a.Pt, h, nullptr, W2, h, c, delta, out, ldo, s);
             }
         }
-        if (st == LT_OK && !sign_path) st = influence_rows(plan, HR, h, Pt, h, nullptr, W2, h, c, delta, out, ldo, s);
-        if (st == LT_OK && !sign_path && info_host) st = lt_plan_info(plan, h, c, info_host, stream);
+        if (st == LT_OK && info_host) {
+            st = lt_plan_info(plan, h, c, info_host, stream);
+            int32_t nf = 0;
+            if (st == LT_OK && a.sign_path && cudaMemcpyAsync(&nf, a.n_fixed, 4, cudaMemcpyDeviceToHost, s) == cudaSuccess &&
+                cudaStreamSynchronize(s) == cudaSuccess)
+                info_host[7] = nf;      // incidences that took the exact (recomputed) path
+        }
     }
     lt_plan_destroy(plan, stream);
     return st;
