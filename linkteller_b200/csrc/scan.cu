@@ -126,21 +126,31 @@ k_scan_lookback(const int32_t* in, int64_t n_in, int32_t* out, int64_t n_out, un
     }
     int32_t total;
     int32_t pre = block_exclusive_scan<int32_t>(sum, total);
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < 32) {
+        // warp 0 looks back 32 descriptors at a time: lane l reads predecessor tile−1−l (spinning until it has
+        // published), the nearest inclusive prefix ends the walk.  One predecessor per step made the last of ~90
+        // resident tiles wait ~90 dependent reads (ncu r1k: 14 µs per mid-sized scan).
+        const int lane = threadIdx.x;
         int32_t excl = 0;
-        if (tile == 0) {
-            atomicExch(&d[0], ((unsigned long long)LB_INCLUSIVE << 32) | (uint32_t)total);
-        } else {
-            atomicExch(&d[tile], ((unsigned long long)LB_AGGREGATE << 32) | (uint32_t)total);
-            for (int32_t t = tile - 1;; --t) {
-                unsigned long long w;
-                do { w = atomicAdd(&d[t], 0ull); } while ((w >> 32) == 0);   // predecessor has not published yet
-                excl += (int32_t)(uint32_t)w;
-                if ((w >> 32) == LB_INCLUSIVE) break;
+        if (tile > 0) {
+            if (lane == 0) atomicExch(&d[tile], ((unsigned long long)LB_AGGREGATE << 32) | (uint32_t)total);
+            for (int32_t t_hi = tile - 1;; t_hi -= 32) {
+                const int32_t t = t_hi - lane;
+                unsigned long long w = (unsigned long long)LB_INCLUSIVE << 32;       // before tile 0: prefix 0
+                if (t >= 0) { do { w = atomicAdd(&d[t], 0ull); } while ((w >> 32) == 0); }
+                const uint32_t incl = __ballot_sync(LT_FULL, (w >> 32) == LB_INCLUSIVE);
+                const int first = __ffs(incl) - 1;                                   // nearest inclusive prefix, if any
+                int32_t val = (first < 0 || lane <= first) ? (int32_t)(uint32_t)w : 0;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(LT_FULL, val, o);
+                excl += val;
+                if (first >= 0) break;
             }
-            atomicExch(&d[tile], ((unsigned long long)LB_INCLUSIVE << 32) | (uint32_t)(excl + total));
         }
-        prefix_s = excl;
+        if (lane == 0) {
+            atomicExch(&d[tile], ((unsigned long long)LB_INCLUSIVE << 32) | (uint32_t)(excl + total));
+            prefix_s = excl;
+        }
     }
     __syncthreads();
     pre += prefix_s;
