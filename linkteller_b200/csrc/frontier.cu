@@ -907,6 +907,24 @@ static int frontier_reduce(const uint64_t* rec_key, const uint64_t* rec_val, con
                            float* out, int64_t ldo, cudaStream_t s) {
     if (M == 0) return LT_OK;
     ProfScope prof2("frontier_reduce", s);
+    // groups above F2_BIG records (a CTA each) write other output pairs than the small groups: they go first, on the
+    // side stream, and run next to the small-group kernel
+    cudaStream_t side = s;
+    if (M > F2_BIG) {
+        cudaStream_t sd = getenv("LT_NO_OVERLAP") ? nullptr : side_stream();
+        if (sd) {
+            cudaEvent_t ev;
+            LT_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            cudaError_t e1 = cudaEventRecord(ev, s);
+            cudaError_t e2 = e1 == cudaSuccess ? cudaStreamWaitEvent(sd, ev, 0) : e1;
+            cudaEventDestroy(ev);
+            if (e2 != cudaSuccess) { set_error("frontier_reduce: fork failed: %s", cudaGetErrorString(e2)); return LT_ERR_CUDA; }
+            side = sd;
+        }
+        k_frontier_reduce_big<<<(unsigned)num_sms() * 2, 32 * F2_BIG_WARPS, 0, side>>>(rec_key, rec_val, grp_off, big, n_big, dq, lddq,
+                                                                                       c, out, ldo);
+        LT_LAUNCH_CHECK();
+    }
 #define LT_F2(G_)                                                                                              \
     k_frontier_reduce<G_><<<(unsigned)ceil_div(M * G_, 256), 256, 0, s>>>(rec_key, rec_val, grp_off, n_groups, dq, lddq, c, out, ldo)
     // lanes per group: a group is a couple of records, so half a warp with up to four columns per lane keeps more
@@ -919,10 +937,13 @@ static int frontier_reduce(const uint64_t* rec_key, const uint64_t* rec_val, con
     else LT_F2(32);
 #undef LT_F2
     LT_LAUNCH_CHECK();
-    if (M > F2_BIG) {
-        k_frontier_reduce_big<<<(unsigned)num_sms() * 2, 32 * F2_BIG_WARPS, 0, s>>>(rec_key, rec_val, grp_off, big, n_big, dq, lddq, c,
-                                                                                    out, ldo);
-        LT_LAUNCH_CHECK();
+    if (side != s) {                                            // join: the big groups ran next to the small ones
+        cudaEvent_t ev;
+        LT_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        cudaError_t e1 = cudaEventRecord(ev, side);
+        cudaError_t e2 = e1 == cudaSuccess ? cudaStreamWaitEvent(s, ev, 0) : e1;
+        cudaEventDestroy(ev);
+        if (e2 != cudaSuccess) { set_error("frontier_reduce: join failed: %s", cudaGetErrorString(e2)); return LT_ERR_CUDA; }
     }
     return LT_OK;
 }

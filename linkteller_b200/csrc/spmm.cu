@@ -125,37 +125,47 @@ k_spmm_vec(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indic
 // rows split over several segments: sum the partial rows in segment order, then bias / ReLU.
 // One warp per row; a lane owns one float4 column slice (d ≤ 128: one pass) and keeps 8 loads in flight —
 // a hub row has hundreds of segments, and one dependent load per segment made this the tail of the SpMM.
-__global__ void k_spmm_fixup(const int32_t* __restrict__ seg_off, const int32_t* __restrict__ sel, int32_t n_rows,
-                             const float* __restrict__ partial, int32_t d, const float* __restrict__ bias, int relu,
-                             float* __restrict__ C, int64_t ldc) {
-    const int lane = threadIdx.x & 31;
-    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (i >= n_rows) return;
-    const int32_t first = seg_off[i], nseg = seg_off[i + 1] - first;
-    if (nseg <= 1) return;
-    const int64_t il = list_pos(sel, i);
-    const int d4 = d >> 2;                                   // the vector path guarantees d % 4 == 0
-    const float4* P4 = reinterpret_cast<const float4*>(partial) + (int64_t)first * d4;
-    for (int col = lane; col < d4; col += 32) {
-        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-        int32_t sgm = 0;
-        for (; sgm + 8 <= nseg; sgm += 8) {
-            float4 p[8];
+__global__ void __launch_bounds__(256)
+k_spmm_fixup(const int32_t* __restrict__ seg_off, const int32_t* __restrict__ sel, int32_t n_rows,
+             const float* __restrict__ partial, int32_t d, const float* __restrict__ bias, int relu,
+             float* __restrict__ C, int64_t ldc) {
+    // a CTA looks at 256 list positions with one thread each and queues the few that span several segments; its
+    // warps then take the queued rows (a warp per position made 45 K CTAs of warps that exit at once on C5)
+    __shared__ int32_t queue[256];
+    __shared__ int32_t n_queued;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) n_queued = 0;
+    __syncthreads();
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n_rows && seg_off[t + 1] - seg_off[t] > 1) queue[atomicAdd(&n_queued, 1)] = (int32_t)t;
+    __syncthreads();
+    const int d4 = d >> 2;                                       // the vector path guarantees d % 4 == 0
+    for (int q = warp; q < n_queued; q += 8) {
+        const int64_t i = queue[q];
+        const int32_t first = seg_off[i], nseg = seg_off[i + 1] - first;
+        const int64_t il = list_pos(sel, i);
+        const float4* P4 = reinterpret_cast<const float4*>(partial) + (int64_t)first * d4;
+        for (int col = lane; col < d4; col += 32) {
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+            int32_t sgm = 0;
+            for (; sgm + 8 <= nseg; sgm += 8) {
+                float4 p[8];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) p[u] = P4[(int64_t)(sgm + u) * d4 + col];
+                for (int u = 0; u < 8; ++u) p[u] = P4[(int64_t)(sgm + u) * d4 + col];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) { a.x += p[u].x; a.y += p[u].y; a.z += p[u].z; a.w += p[u].w; }
+                for (int u = 0; u < 8; ++u) { a.x += p[u].x; a.y += p[u].y; a.z += p[u].z; a.w += p[u].w; }
+            }
+            for (; sgm < nseg; ++sgm) {
+                const float4 p = P4[(int64_t)sgm * d4 + col];
+                a.x += p.x; a.y += p.y; a.z += p.z; a.w += p.w;
+            }
+            if (bias) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(bias) + col);
+                a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+            }
+            if (relu) { a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f); }
+            reinterpret_cast<float4*>(C + il * ldc)[col] = a;
         }
-        for (; sgm < nseg; ++sgm) {
-            const float4 p = P4[(int64_t)sgm * d4 + col];
-            a.x += p.x; a.y += p.y; a.z += p.z; a.w += p.w;
-        }
-        if (bias) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(bias) + col);
-            a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
-        }
-        if (relu) { a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f); }
-        reinterpret_cast<float4*>(C + il * ldc)[col] = a;
     }
 }
 
@@ -449,7 +459,7 @@ int spmm_csr_f32_seg(const int32_t* indptr, const int32_t* indices, const float*
 #undef LT_SPMM_V
         LT_LAUNCH_CHECK();
         if (multi) {
-            k_spmm_fixup<<<(unsigned)ceil_div((int64_t)n_list * 32, 256), 256, 0, s>>>(seg_off, sel, n_list, partial, d, bias,
+            k_spmm_fixup<<<(unsigned)ceil_div((int64_t)n_list, 256), 256, 0, s>>>(seg_off, sel, n_list, partial, d, bias,
                                                                                      relu, C, ldc);
             LT_LAUNCH_CHECK();
         }
@@ -531,7 +541,7 @@ int spmm_csr_f32_seg(const int32_t* indptr, const int32_t* indices, const float*
             LT_LAUNCH_CHECK();
         }
         if (multi) {
-            k_spmm_fixup<<<(unsigned)ceil_div((int64_t)n_long * 32, 256), 256, 0, s>>>(off_long, sel_long, n_long, partial, d,
+            k_spmm_fixup<<<(unsigned)ceil_div((int64_t)n_long, 256), 256, 0, s>>>(off_long, sel_long, n_long, partial, d,
                                                                                      bias, relu, C, ldc);
             LT_LAUNCH_CHECK();
         }
