@@ -55,9 +55,8 @@ int tc_prepack_b(const float* B, int64_t ldb, int transB, int32_t N, int32_t K, 
 
 // LT_TC_WS=0 selects the lock-step kernel (k_gemm_tc) instead of the warp-specialised one (k_gemm_ws)
 bool tc_use_ws() {
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("LT_TC_WS"); v = (e && e[0] == '0') ? 0 : 1; }
-    return v == 1;
+    const char* e = getenv("LT_TC_WS");
+    return !(e && e[0] == '0');
 }
 
 // handled = false ⇒ the caller uses the fp32 SIMT kernel (tiny problems are not worth a tensor-core launch)
