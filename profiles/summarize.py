@@ -6,7 +6,7 @@
     python profiles/summarize.py stalls <report.ncu-rep> [n]                # stall reasons + hottest SASS lines
 
 `launches` reads the CSV of  ncu --metrics gpu__time_duration.sum --clock-control none --csv ;
-with --last-step only the launches after the last lt::k_tmap (= the last attack in the capture)
+with --last-step only the launches after the last lt::k_test_lens (= the last attack in the capture)
 are counted.  Only kernels of this library (namespace lt::) are listed individually.
 """
 import csv
@@ -48,7 +48,7 @@ def launches(path, last_step):
             v *= 1e3
         rows.append((short(r["Kernel Name"]), v))
     if last_step:
-        idx = [i for i, (k, _) in enumerate(rows) if k.startswith("lt::k_tmap")]
+        idx = [i for i, (k, _) in enumerate(rows) if k.startswith("lt::k_test_lens")]
         if idx:
             rows = rows[idx[-1]:]
     agg = OrderedDict()
