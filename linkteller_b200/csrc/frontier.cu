@@ -100,10 +100,10 @@ __global__ void k_mark_rows(const int32_t* __restrict__ indptr, const int32_t* _
     for (int32_t k = indptr[v] + lane; k < indptr[v + 1]; k += 32) flag[indices[k]] = 1;
 }
 
-// pos = exclusive scan of flag.  rmap[r] = compact index or -1; rows[compact] = r; rlen[compact] = nnz(row r)
+// pos = exclusive scan of flag.  rmap[r] = compact index or -1; rows[compact] = r; nseg[compact] = SpMM segments of row r
 __global__ void k_compact_rows(const int32_t* __restrict__ flag, const int32_t* __restrict__ pos, int32_t n,
                                const int32_t* __restrict__ indptr, int32_t* __restrict__ rmap,
-                               int32_t* __restrict__ rows, int32_t* __restrict__ rlen, int32_t* __restrict__ nseg) {
+                               int32_t* __restrict__ rows, int32_t* __restrict__ nseg) {
     int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n) return;
     if (flag[r]) {
@@ -111,7 +111,6 @@ __global__ void k_compact_rows(const int32_t* __restrict__ flag, const int32_t* 
         rmap[r] = p;
         rows[p] = (int32_t)r;
         const int32_t len = indptr[r + 1] - indptr[r];
-        rlen[p] = len;
         nseg[p] = len <= SPMM_SEG ? 1 : (len + SPMM_SEG - 1) / SPMM_SEG;
     } else {
         rmap[r] = -1;
@@ -637,15 +636,13 @@ static int plan_build(lt_plan* p, const int32_t* indptr, const int32_t* indices,
     const int32_t n = p->n, T = p->T, lo = p->lo, Ts = p->Ts;
     Scratch scratch(s);
     struct ScopeBox { ProfScope* p; ~ScopeBox() { delete p; } void end() { delete p; p = nullptr; } } prof_a{new ProfScope("plan", s)};
-    int32_t *tmap, *rmap, *flag, *all_len, *rlen;
+    int32_t *tmap, *rmap, *flag, *all_len;
     int* err;
-    int64_t* sums;  // [0]=Σ all_len  [1]=Σ rlen
     LT_TRY(scratch.alloc(&tmap, (size_t)n));
     LT_TRY(scratch.alloc(&rmap, (size_t)n));
     LT_TRY(scratch.alloc(&flag, (size_t)n + 1));
     LT_TRY(scratch.alloc(&all_len, (size_t)T + 1));
     LT_TRY(scratch.alloc(&err, 1));
-    LT_TRY(scratch.alloc(&sums, 2));
     LT_TRY(plan_alloc(p, &p->s_indptr, (size_t)Ts + 1, s));
     LT_CUDA(cudaMemsetAsync(flag, 0, ((size_t)n + 1) * 4, s));
     LT_CUDA(cudaMemsetAsync(err, 0, sizeof(int), s));
@@ -680,9 +677,8 @@ static int plan_build(lt_plan* p, const int32_t* indptr, const int32_t* indices,
     const int64_t E = p->E;
 
     LT_TRY(plan_alloc(p, &p->rows, (size_t)R, s));
-    LT_TRY(scratch.alloc(&rlen, (size_t)R + 1));
     LT_TRY(plan_alloc(p, &p->seg_off, (size_t)R + 1, s));
-    k_compact_rows<<<(unsigned)ceil_div(n, 256), 256, 0, s>>>(flag, pos, n, indptr, rmap, p->rows, rlen, p->seg_off);
+    k_compact_rows<<<(unsigned)ceil_div(n, 256), 256, 0, s>>>(flag, pos, n, indptr, rmap, p->rows, p->seg_off);
     LT_LAUNCH_CHECK();
     LT_TRY(exclusive_scan_i32(p->seg_off, p->seg_off, R, s));
     p->total_seg = (int64_t)h_seg_tot[0];
