@@ -115,3 +115,23 @@ def test_dp_host_halves_match_oracle_streams(golden):
     noise, n_keep = dp.lapgraph_noise(n, len(g["a1_data"]) // 2, float(g["epsilon"]), 42)
     assert noise.shape == (n, n) and n_keep == O.lapgraph(g["a1_indptr"], g["a1_indices"], g["a1_data"], n,
                                                           float(g["epsilon"]), 42)[3]
+
+
+def test_model_dispatch_and_hidden_padding():
+    """Weight tuples select the model (4: GCN, 6: GCN3, else the reference's NotImplementedError, gcn_trainer.py:88);
+    first-hidden widths that are not multiples of 4 are padded with units that never fire."""
+    import torch
+    from linkteller_b200 import ops
+    with pytest.raises(NotImplementedError):
+        ops.model_forward(None, None, [torch.zeros(1)] * 8)
+    with pytest.raises(NotImplementedError):
+        ops.attack_rows(None, None, [torch.zeros(1)] * 2, None, 1e-4)
+    g = torch.Generator().manual_seed(0)
+    w1, b1, w2 = torch.randn(7, 10, generator=g), torch.randn(10, generator=g), torch.randn(10, 3, generator=g)
+    p1, pb, p2 = ops._pad_first_hidden(w1, b1, w2)
+    assert p1.shape == (7, 12) and pb.shape == (12,) and p2.shape == (12, 3)
+    x = torch.randn(5, 7, generator=g)
+    ref = torch.relu(x @ w1 + b1) @ w2
+    assert torch.allclose(torch.relu(x @ p1 + pb) @ p2, ref, atol=1e-6)
+    q1, qb, q2 = ops._pad_first_hidden(p1, pb, p2)                    # already a multiple of 4: returned as is
+    assert q1 is p1 and qb is pb and q2 is p2
