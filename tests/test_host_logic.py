@@ -135,3 +135,35 @@ def test_model_dispatch_and_hidden_padding():
     assert torch.allclose(torch.relu(x @ p1 + pb) @ p2, ref, atol=1e-6)
     q1, qb, q2 = ops._pad_first_hidden(p1, pb, p2)                    # already a multiple of 4: returned as is
     assert q1 is p1 and qb is pb and q2 is p2
+
+
+def _model_worker(rank, world, T, n_weights, port, ok):
+    """influence_matrix_model at world_size 2 on CPU tensors: the C call is replaced by a stand-in that fills the
+    rows [lo,hi) it is asked for, so the slicing, the weight-tuple dispatch and the all-gather are what is tested."""
+    import torch.distributed as dist
+    from linkteller_b200 import ops
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    full = torch.arange(T * T, dtype=torch.float32).reshape(T, T) + 0.5
+    calls = []
+
+    def fake_rows(adj, x, weights, test_nodes, delta, lo=0, hi=None, out=None, want_info=False):
+        assert len(weights) == n_weights and out.shape == (hi - lo, T)
+        calls.append((lo, hi))
+        out.copy_(full[lo:hi])
+        return out
+    ops.attack_rows = fake_rows
+    tn = torch.arange(T, dtype=torch.int32)
+    got = attack.influence_matrix_model(None, torch.zeros(1), [torch.zeros(1)] * n_weights, tn, 1e-4)
+    ok[rank] = int(torch.equal(got, full) and calls == [attack.slice_bounds(T, world, rank)])
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("T,n_weights", [(8, 4), (9, 6)])       # GCN with equal slices, GCN3 with ragged slices
+def test_influence_matrix_model_gloo_world2(T, n_weights):
+    import torch.multiprocessing as mp
+    ok = mp.get_context("spawn").Array("i", [0, 0])
+    port = 30100 + (os.getpid() + T) % 500
+    mp.spawn(_model_worker, args=(2, T, n_weights, port, ok), nprocs=2, join=True)
+    assert list(ok) == [1, 1]
