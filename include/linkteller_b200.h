@@ -124,7 +124,12 @@ int lt_gcn_forward(const int32_t* indptr, const int32_t* indices, const float* v
  *  P[p_index ? p_index[j] : j, :].  out is [hi-lo, T] float32 with leading dimension ldo and is
  *  fully overwritten (zeros included).
  *
- *  lt_attack_efficient = plan + restricted precompute of H_R / P + lt_influence_rows in one call.
+ *  lt_attack_efficient = plan + restricted precompute of H_R / P + lt_influence_rows in one call.  When the
+ *  products are large enough for the tensor cores it keeps only the signs of H_R (one bit per element and the
+ *  row's smallest magnitude) and recomputes the rows where a ReLU can switch exactly; the precompute is enqueued
+ *  on the caller's stream as soon as the frontier rows are known, while the rest of the plan runs on an
+ *  internal high-priority stream that is joined back before the frontier kernels (to the caller all work
+ *  stays ordered on the stream passed in).
  * ------------------------------------------------------------------------------------------- */
 int lt_plan_create(const int32_t* indptr, const int32_t* indices, const float* values, int32_t n,
                    const int32_t* test_nodes, int32_t T, int32_t lo, int32_t hi, lt_stream_t stream,
