@@ -316,6 +316,14 @@ def main():
                         "frac": achieved / peak, "traffic": None, "traffic_source": None, "peak_source": peak_src,
                         "algorithmic_bytes_per_launch": int(alg[dom]), "launch_ms": dur_ms,
                         "share_of_step": per_step[dom] / (ms / args.steps)}
+            if dom in ("spmm_ax", "spmm_h"):
+                # SURVEY.md §8d asks for both figures: `achieved` uses the compulsory bytes (every gathered row once),
+                # the gather figure counts every gathered row as moved (no reuse) — the bytes the kernel really requests
+                d_feat = f if dom == "spmm_ax" else h
+                gather = nnzR * (8 + 4 * d_feat) + 8 * R + 4 * d_feat * R
+                roofline["gather_bytes_per_launch"] = int(gather)
+                roofline["achieved_gather"] = gather / (dur_ms / 1e3) / 1e9
+                roofline["frac_gather"] = roofline["achieved_gather"] / peak
             hit = NCU_TRAFFIC.get((args.workload, world, dom)) if args.n_test is None else None
             if hit:
                 roofline["traffic"], roofline["traffic_source"] = hit
