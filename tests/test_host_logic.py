@@ -167,3 +167,18 @@ def test_influence_matrix_model_gloo_world2(T, n_weights):
     port = 30100 + (os.getpid() + T) % 500
     mp.spawn(_model_worker, args=(2, T, n_weights, port, ok), nprocs=2, join=True)
     assert list(ok) == [1, 1]
+
+
+def test_profile_summary_tool_reads_the_committed_launch_list():
+    """profiles/summarize.py turns the committed ncu launch list of one attack into per-kernel shares."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "profiles", "summarize.py"), "launches",
+                          os.path.join(root, "profiles", "r1m_launches_large.csv"), "--last-step"],
+                         capture_output=True, text=True, check=True).stdout
+    lines = [ln for ln in out.splitlines() if ln.startswith("lt::")]
+    assert lines and lines[0].startswith("lt::k_spmm_vec")          # the SpMM is the largest share of the step
+    share = float(lines[0].split()[-1].rstrip("%"))
+    assert 50.0 < share < 90.0
+    assert any(ln.startswith("lt::k_gemm_ws") for ln in lines) and any(ln.startswith("lt::k_scan_lookback") for ln in lines)
