@@ -406,7 +406,7 @@ def balanced_edge_sets(indptr, indices, sample_seed):
 def _grad_mat(x, adj, w, v, delta):
     pert = torch.zeros_like(x)
     pert[v] = x[v] * delta
-    return (gcn_forward(x + pert, adj, *w) - gcn_forward(x, adj, *w)) / delta
+    return (model_forward(x + pert, adj, *w) - model_forward(x, adj, *w)) / delta
 
 
 def _tensors(X, coo, weights, n, dtype):

@@ -172,3 +172,38 @@ def test_attacker_gcn3_end_to_end(golden, tmp_path, monkeypatch):
     with torch.no_grad():
         z = model(feats, adj_t).cpu().numpy()
     assert np.abs(z - g["logits"]).max() <= 2e-4 * max(1.0, np.abs(g["logits"]).max())
+
+
+def test_attacker_gcn3_balanced_full_and_naive(golden, tmp_path, monkeypatch):
+    """GCN3 with --sample-type balanced-full (attacker.py:250-284) and the naive per-pair attack (:143-206): listed
+    pairs read from blocks of three-hop influence rows, against the oracle in float64."""
+    from linkteller_b200 import adj as A, gcn
+    from linkteller_b200.attacker import Attacker
+    g = golden("tiny_gcn3")
+    s, w, (ip, ix, dv), coo = problem3(g)
+    model = gcn.GCN3(s.f, int(g["h1"]), int(g["h2"]), s.c, 0.5)
+    model.load_state_dict({k: torch.from_numpy(a) for k, a in zip(KEYS, w)})
+    model = model.cuda().eval()
+    adj_ori = sp.csr_matrix((dv, ix, ip), shape=(s.n, s.n))
+    r, c, v = coo
+    adj_t = A.sparse_mx_to_torch_sparse_tensor(sp.coo_matrix((v, (r, c)), shape=(s.n, s.n))).cuda()
+    feats = torch.from_numpy(s.features).cuda()
+    worker = types.SimpleNamespace(n_nodes=s.n, n_features=s.f, features=feats, adj_full=adj_t, features_2=feats,
+                                   adj_2=adj_t, adj_ori=adj_ori)
+    args = types.SimpleNamespace(dataset="twitch/ES/RU", sample_type="balanced-full", n_test=0, influence=1e-4,
+                                 sample_seed=42, mode="vanilla-clean", attack_mode="efficient", perturb_type=None,
+                                 epsilon=5.0, noise_seed=42, n_layer=3)
+    monkeypatch.chdir(tmp_path)
+    att = Attacker(args, model, worker)
+    att.prepare_test_data()
+    ex, ne = np.asarray(att.exist_edges), np.asarray(att.nonexist_edges)
+    cap = {}
+    att.compute_and_save = lambda e, n_, **k: cap.update(e=np.asarray(e), ne=np.asarray(n_))
+    att.link_prediction_attack_efficient_balanced()
+    e64, n64 = O.efficient_balanced_scores(s.features, coo, w, s.n, ex, ne, 1e-4, torch.float64)
+    close_to_ref64(cap["e"], e64)
+    close_to_ref64(cap["ne"], n64)
+    att.link_prediction_attack()                                   # naive: perturb the SECOND node of a pair
+    e64, n64 = O.naive_scores(s.features, coo, w, s.n, ex, ne, 1e-4, torch.float64)
+    close_to_ref64(cap["e"], e64)
+    close_to_ref64(cap["ne"], n64)
