@@ -45,13 +45,14 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "reference-cuda"])
     ap.add_argument("--workload", default="large", choices=["large", "flickr", "ppi", "twitch", "small", "tiny"])
     ap.add_argument("--n-test", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="target CPU time of the cpu_baseline sample")
-    ap.add_argument("--ref-budget", type=float, default=240.0, help="wall-clock cap of the reference arm (s)")
+    ap.add_argument("--ref-budget", type=float, default=330.0, help="wall-clock cap of the reference arm's probe + warm-up + timed steps (s)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the parity_check / cpu_baseline legs")
     return ap.parse_args()
 
 
@@ -125,71 +126,124 @@ def peaks():
 
 
 # ----------------------------------------------------------------------------------------- reference arm
-def host_problem(wl):
-    """Host copies of the workload in the form the reference holds them (torch COO pieces, numpy)."""
-    import torch
-    hat = wl.adj_hat
-    indptr = hat.indptr.cpu().numpy()
-    row = np.repeat(np.arange(wl.n, dtype=np.int64), np.diff(indptr))
-    coo = (row, hat.indices.cpu().numpy().astype(np.int64), hat.values.cpu().numpy())
-    weights = [t.cpu().numpy() for t in (wl.w1, wl.b1, wl.w2, wl.b2)]
-    return wl.x.cpu().numpy(), coo, weights, wl.test_nodes.cpu().numpy().astype(np.int64)
+def bench_config(desc: dict, world: int) -> dict:
+    """The `config` object of the JSON line — the same for the product arm and the reference arm."""
+    ws = working_set_bytes(desc)
+    l2 = (f"inputs (X + Â = {ws / 2**20:.0f} MB) exceed the 126 MB L2; no explicit flush between steps" if not needs_flush(desc)
+          else f"inputs (X + Â = {ws / 2**20:.0f} MB) could stay in the 126 MB L2: a 512 MB buffer is written between steps, outside the per-step timers")
+    return dict(desc, parallelism=f"rows sharded over {world} GPU(s), graph replicated", l2=l2)
 
 
-def cpu_rows_per_s(wl, target_seconds, max_rows=None):
-    """The reference's per-row work on the host cores (oracle port; the one place bench.py runs oracle/)."""
-    import torch
-    from oracle import lt_oracle as O
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    X, coo, weights, tn = host_problem(wl)
-    nnz = len(coo[0])
-    # rough per-row cost model (s): two forwards, ~0.5 µs per non-zero for the 256-wide COO spmm
-    est = 2.0 * (nnz * 0.6e-6 + wl.n * wl.f * wl.h * 2 / 2e11)
-    if est > 1.5 * target_seconds:
-        slice_div = int(min(64, max(2, round(est / (0.6 * target_seconds)))))
-        n_rows = 1
-    else:
-        slice_div = 1
-        n_rows = int(max(1, min(wl.T, target_seconds / max(est, 1e-3))))
-    if max_rows:
-        n_rows = min(n_rows, max_rows)
-    per_row, what = O.time_reference_rows(X, coo, weights, wl.n, tn, wl.delta, n_rows, slice_div=slice_div,
-                                          threads=cores)
-    return 1.0 / per_row, cores, what
+def working_set_bytes(desc: dict) -> int:
+    return desc["n"] * desc["f"] * 4 + desc["nnz_adj_hat"] * 8
 
 
-def run_reference(args, rank, world):
-    """--impl reference: the reference's own CPU implementation of the path (oracle port — the
-    reference is pure Python over torch CPU ops; its modules cannot travel to the GPU box) on the
-    host cores, same workload / metric / unit.  Rank 0 only."""
+def needs_flush(desc: dict) -> bool:
+    return working_set_bytes(desc) < (512 << 20)
+
+
+def time_reference(runner, T, steps, warmup, budget_s, step_seconds):
+    """Time the reference's loop body (attacker.py:220-229) in steps of `rows_per_step` influence rows.
+
+    One row is probed first (it doubles as warm-up: the CPU path has no clocks to ramp, only pages to fault in);
+    rows_per_step is then sized so that a step costs about `step_seconds`, at least one full row and at most one
+    whole attack (T rows).  Warm-up and timed steps are cut short only by the wall-clock budget — the counts
+    actually run are the ones reported."""
+    t_begin = time.time()
+    _, t_probe = runner.rows([0])
+    rows_per_step = int(max(1, min(T, step_seconds / max(t_probe, 1e-6))))
+    est = t_probe * rows_per_step
+    nxt = 1
+
+    def take():
+        nonlocal nxt
+        idx = [(nxt + k) % T for k in range(rows_per_step)]
+        nxt = (nxt + rows_per_step) % T
+        return idx
+    done_w = 1 if rows_per_step == 1 else 0          # the probe row was a whole step
+    while done_w < warmup and (time.time() - t_begin) + est * 2 <= budget_s * 0.35:
+        runner.rows(take())
+        done_w += 1
+    times = []
+    while len(times) < steps and (not times or (time.time() - t_begin) + est <= budget_s):
+        _, dt = runner.rows(take())
+        times.append(dt)
+        est = sum(times) / len(times)
+    return rows_per_step, times, done_w, t_probe
+
+
+def run_reference(args, rank, world, cuda=False):
+    """--impl reference: the UNMODIFIED reference (oracle/_ref: gcn.models.GCN, Attacker.get_gradient_eps_mat and
+    the T `.norm().item()` calls per row, attacker.py:100-108, 220-229) on the host cores, on inputs built with
+    numpy / torch only (oracle/refgen.py) — the product's CUDA library is never loaded in this process.
+    --impl reference-cuda: the same code through the reference's own `.cuda()` placement (what an un-accelerated
+    user of the reference gets on this GPU: cuBLAS sgemm + cuSPARSE).  Rank 0 only."""
     if rank != 0:
         return
     import torch
-    from linkteller_b200 import workloads
-    wl = workloads.make(args.workload, device="cuda" if torch.cuda.is_available() else "cpu", n_test=args.n_test)
-    t_start = time.time()
-    vals, what, cores = [], "", os.cpu_count() or 1
-    budget = args.ref_budget
-    per_step = max(2.0, min(args.cpu_seconds, budget / max(1, args.steps + min(args.warmup, 1))))
-    done_w = 0
-    for _ in range(min(args.warmup, 1)):                  # CPU path: one warm-up pass is enough to page in
-        cpu_rows_per_s(wl, per_step, max_rows=4)
-        done_w += 1
-    for _ in range(args.steps):
-        v, cores, what = cpu_rows_per_s(wl, per_step)
-        vals.append(v)
-        if time.time() - t_start > budget:
-            break
-    value = float(len(vals) / sum(1.0 / v for v in vals))   # total rows / total time
-    cfg = wl.describe()
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-            "steps": len(vals), "warmup": done_w, "ms_per_step": 1e3 * wl.T / value, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": what},
+    from oracle import refgen
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    prob = refgen.host_problem(args.workload, n_test=args.n_test)
+    runner, kind = refgen.make_runner(prob, device="cuda" if cuda else "cpu", threads=cores)
+    step_seconds = min(args.cpu_seconds, args.ref_budget / max(1, args.steps + args.warmup))
+    rows_per_step, times, done_w, t_probe = time_reference(runner, prob.T, args.steps, args.warmup, args.ref_budget,
+                                                           step_seconds)
+    total_rows = rows_per_step * len(times)
+    value = total_rows / sum(times)
+    sample = (f"{len(times)} timed step(s) of {rows_per_step} full influence row(s) each (2 GCN forwards + {prob.T} norms per row, "
+              f"no slicing) after {done_w} warm-up step(s) + 1 probe row; requested steps={args.steps} warmup={args.warmup}"
+              + (f", cut by the {args.ref_budget:.0f} s wall-clock budget" if len(times) < args.steps or done_w < args.warmup else "")
+              + f"; {runner.what}; inputs: {prob.generator}")
+    line = {"impl": "reference-cuda" if cuda else "reference", "metric": METRIC, "value": value, "unit": UNIT,
+            "n_gpus": args.gpus, "steps": len(times), "warmup": done_w, "ms_per_step": 1e3 * sum(times) / len(times),
+            "rows_per_step": rows_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": bench_config(prob.describe(), args.gpus),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
+    if cuda:
+        line["cpu_baseline"]["device"] = torch.cuda.get_device_name(0)
     print(json.dumps(line), flush=True)
+
+
+def cpu_legs(wl, info, infl, args):
+    """cpu_baseline + parity_check of the product arm's line (rank 0, N = 1): one host copy of the inputs feeds both.
+    cpu_baseline: the reference's loop body from oracle/_ref on the host cores, a bounded sample of full rows.
+    parity_check: ≥ 16 influence rows of the matrix just timed (hub rows + seeded random rows) against the
+    float64 sub-problem oracle (oracle.LocalInfluence) — the oracle is the checker here, never the thing measured."""
+    import torch
+    from oracle import lt_oracle as O
+    from oracle import refgen
+    cores = os.cpu_count() or 1
+    prob = refgen.host_problem_from_workload(wl)
+    out = {}
+    # ---- parity_check
+    ip = wl.adj_hat.indptr.cpu().numpy()
+    rows = O.pick_parity_rows(ip, prob.test_nodes, n_hub=4, n_rand=12)
+    t0 = time.time()
+    loc = O.LocalInfluence(ip, prob.coo[1], prob.coo[2], prob.X, prob.weights, prob.test_nodes)
+    ref, mask, hits = loc.rows(rows, wl.delta)
+    got = infl[torch.from_numpy(rows).to(infl.device)].cpu().numpy().astype(np.float64)
+    same, rel = O.compare_rows(got, ref)
+    out["parity_check"] = {"rows": int(len(rows)), "support_equal": bool(same), "max_rel": rel, "tolerance": 1e-3,
+                           "ok": bool(same and rel <= 1e-3), "rows_through_exact_fixup": int((hits > 0).sum()),
+                           "oracle": "oracle.LocalInfluence float64 (2-hop sub-problem, pinned to the reference's float64 run)",
+                           "seconds": round(time.time() - t0, 1)}
+    del loc
+    # ---- cpu_baseline
+    if not args.no_cpu_baseline:
+        runner, kind = refgen.make_runner(prob, device="cpu", threads=cores)
+        _, t_probe = runner.rows([0])
+        k = int(max(0, min(wl.T - 1, (args.cpu_seconds - t_probe) / max(t_probe, 1e-6))))
+        if k >= 1:
+            _, dt = runner.rows(list(range(1, 1 + k)))
+            value, sample = k / dt, f"{k} full rows after 1 warm-up row"
+        else:
+            value, sample = 1.0 / t_probe, "1 full row, no warm-up (one row exceeds the sample budget)"
+        out["cpu_baseline"] = {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
+                               "sample": f"{sample}; {runner.what}; 2 GCN forwards + {wl.T} norms per row, no slicing"}
+    return out
 
 
 # ----------------------------------------------------------------------------------------- our arm
@@ -198,8 +252,8 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.impl == "reference":
-        return run_reference(args, rank, world)
+    if args.impl in ("reference", "reference-cuda"):
+        return run_reference(args, rank, world, cuda=args.impl == "reference-cuda")
 
     import torch
     import torch.distributed as dist
@@ -216,14 +270,20 @@ def main():
     wl = workloads.make(args.workload, device=dev, n_test=args.n_test)
     T = wl.T
     out = torch.empty((T, T), dtype=torch.float32, device=dev)
+    group = dist.group.WORLD if world > 1 else None
 
     def step():
-        return attack.influence_matrix(wl.adj_hat, wl.x, wl.w1, wl.b1, wl.w2, wl.test_nodes, wl.delta, out=out)
+        return attack.influence_matrix(wl.adj_hat, wl.x, wl.w1, wl.b1, wl.w2, wl.test_nodes, wl.delta, out=out, group=group)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    # Timing rules: inputs larger than the L2 need no flush (the default workload: X 0.98 GB + Â 1.5 GB against 126 MB);
+    # smaller workloads get a 512 MB write between steps, outside the per-step event pairs.
+    flush = needs_flush(wl.describe())
+    flush_buf = torch.empty(512 << 20, dtype=torch.uint8, device=dev) if flush else None
 
     for _ in range(max(args.warmup, 3)):
         step()
@@ -234,15 +294,27 @@ def main():
     if rank == 0:
         sampler.start()
     launches0 = ops.launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ops.profile() as prof:
         barrier()
-        ev0.record()
-        for _ in range(args.steps):
-            step()
-        ev1.record()
-        barrier()
-    ms = ev0.elapsed_time(ev1)
+        if flush:
+            evs = []
+            for _ in range(args.steps):
+                flush_buf.fill_(1)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                step()
+                e1.record()
+                evs.append((e0, e1))
+            barrier()
+            ms = sum(a.elapsed_time(b) for a, b in evs)
+        else:
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+            for _ in range(args.steps):
+                step()
+            ev1.record()
+            barrier()
+            ms = ev0.elapsed_time(ev1)
     launches = ops.launch_count() - launches0
     if world > 1:
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
@@ -266,7 +338,6 @@ def main():
         host = {k: stage.adopt(k, v.cpu(), dev) for k, v in
                 (("indptr", hat.indptr), ("indices", hat.indices), ("values", hat.values), ("x", wl.x), ("w1", wl.w1),
                  ("b1", wl.b1), ("w2", wl.w2), ("test_nodes", wl.test_nodes))}
-        group = dist.group.WORLD if world > 1 else None
 
         def host_step():
             return attack.influence_matrix_host(host["indptr"], host["indices"], host["values"], host["x"], host["w1"],
@@ -289,20 +360,26 @@ def main():
             ems = float(t.item())
         e2e = {"value": k_e2e * T / (ems / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "steps": k_e2e, "ms_per_step": ems / k_e2e}
+        del stage, host
 
     if rank == 0:
         peak, peak_src = peaks()
         h, c, f = wl.h, wl.c, wl.f
+        Ts = hi - lo
         R, E, M, nnzR = info["frontier_rows"], info["incidences"], info["records"], info["frontier_row_nnz"]
-        # algorithmic bytes per launch of each kernel family (DESIGN.md §kernels)
+        pairs = info["support_pairs"]
+        sign_path = info["exact_path_incidences"] >= 0 and "gemm_h" in phases and f < h and E * h * c >= (1 << 24) and R * h * f >= (1 << 24)
+        wpr = (h + 31) // 32
+        # algorithmic bytes per launch of each kernel family (DESIGN.md §4)
+        dq_in = E * (4 * wpr + 4 + 12) if sign_path else E * (4 * h + 12)      # sign words + min|H| + (j,ρ,a), or one H row
         alg = {
             "spmm_ax": 8 * nnzR + 8 * R + 4 * f * min(wl.n, nnzR) + 4 * f * R,
             "spmm_h": 8 * nnzR + 8 * R + 4 * h * min(wl.n, nnzR) + 4 * h * R,
-            "gemm_h": 4 * (R * f + f * h + R * h),
+            "gemm_h": 4 * (R * f + f * h) + (R * (4 * wpr + 4) if sign_path else 4 * R * h),
             "gemm_p": 4 * (wl.n * f + f * h + wl.n * h),
-            "gemm_pv": 4 * ((hi - lo) * f + f * h + (hi - lo) * h),
-            "frontier_dq": E * (4 * h + 12 + 4 * c) + (hi - lo) * 4 * h + 4 * h * c,
-            "frontier_reduce": M * 16 + E * 4 * c + 4 * info["support_pairs"],
+            "gemm_pv": 4 * (Ts * f + f * h + Ts * h),
+            "frontier_dq": dq_in + E * 4 * c + Ts * 4 * h + 4 * h * c,
+            "frontier_reduce": M * 16 + E * 4 * c + 4 * pairs,
         }
         per_step = {k: v[1] / args.steps for k, v in phases.items()}
         kern = {k: v for k, v in per_step.items() if k in alg}
@@ -327,22 +404,46 @@ def main():
             hit = NCU_TRAFFIC.get((args.workload, world, dom)) if args.n_test is None else None
             if hit:
                 roofline["traffic"], roofline["traffic_source"] = hit
-                # the same launch against the bytes it really moves (gathered rows are re-fetched: L2 hit rate 10 %)
+                # the same launch against the bytes it really moves
                 roofline["dram_frac_of_peak"] = hit[0] / (dur_ms / 1e3) / 1e9 / peak
+        # ---- the frontier-propagation kernels (north_star's "≥ 50 % of the HBM roofline" target): F1 + F2 together
+        roofline_frontier = None
+        t_front = per_step.get("frontier_dq", 0.0) + per_step.get("frontier_reduce", 0.0)
+        if t_front > 0:
+            ip = wl.adj_hat.indptr.long()
+            deg = ip[1:] - ip[:-1]
+            v = wl.test_nodes[lo:hi].long()
+            nhat = deg[v]
+            starts = ip[v]
+            offs = torch.cumsum(nhat, 0) - nhat
+            idx = torch.repeat_interleave(starts - offs, nhat) + torch.arange(int(nhat.sum()), device=dev)
+            hop2 = int(deg[wl.adj_hat.indices[idx].long()].sum())
+            # B_row(v) = 4h(1+|N̂(v)|) + 8|N̂(v)| + 12·Σ_{r∈N̂(v)}|N̂(r)| + 4T, summed exactly over the slice
+            survey = int(4 * h * (Ts + int(nhat.sum())) + 8 * int(nhat.sum()) + 12 * hop2 + 4 * T * Ts)
+            needed = int(alg["frontier_dq"] + alg["frontier_reduce"])
+            roofline_frontier = {
+                "bound": "hbm", "kernels": "frontier_dq (F1) + frontier_reduce (F2)", "ms": t_front, "peak": peak, "unit": "GB/s",
+                "survey_bytes": survey, "achieved_survey": survey / (t_front / 1e3) / 1e9,
+                "frac_survey": survey / (t_front / 1e3) / 1e9 / peak,
+                "needed_bytes": needed, "achieved": needed / (t_front / 1e3) / 1e9, "frac": needed / (t_front / 1e3) / 1e9 / peak,
+                "note": "survey_bytes = Σ_v B_row(v) of SURVEY.md §8(d), which charges one 4h-byte H row per incidence and 12 B per "
+                        "second-hop entry; needed_bytes = what this implementation must move (sign words instead of H rows, "
+                        "records only for test-node observers)"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": dict(wl.describe(), parallelism=f"rows sharded over {world} GPU(s), graph replicated",
-                           l2="inputs (X, Â, H_R) exceed the 126 MB L2; no explicit flush between steps"),
+            "config": bench_config(wl.describe(), world),
+            "l2_flush_between_steps": bool(flush),
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-            "roofline": roofline,
+            "roofline": roofline, "roofline_frontier": roofline_frontier,
             "phases_ms_per_step": {k: round(v, 4) for k, v in per_step.items()},
             "plan": {k: int(v) for k, v in info.items()},
         }
-        if world == 1 and not args.no_cpu_baseline:
-            v, cores, what = cpu_rows_per_s(wl, args.cpu_seconds)
-            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": what}
+        if world == 1 and not args.no_parity:
+            step()
+            torch.cuda.synchronize()
+            line.update(cpu_legs(wl, info, out, args))
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

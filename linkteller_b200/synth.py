@@ -115,3 +115,65 @@ def gcn3_weights(f: int, h1: int, h2: int, c: int, seed: int = 42):
         out.append(rng.uniform(-s, s, (fin, fout)).astype(np.float32))
         out.append(rng.uniform(-s, s, fout).astype(np.float32))
     return tuple(out)
+
+
+# ---------------------------------------------------------------------------------- shared by the product arm
+# (linkteller_b200.workloads) and the reference arm of bench.py (oracle/refgen.py): nothing here touches the CUDA library
+def chung_lu_edges_device(n: int, m: int, seed: int, device, alpha: float = 0.5):
+    """~m undirected edges [k,2] int64 (self loops removed, repeats possible — the CSR build
+    collapses them with binarize=True) of a power-law expected-degree graph; node ids are scattered
+    by a random permutation so degree does not correlate with the id."""
+    import torch
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    inv = 1.0 / (1.0 - alpha)
+    k = int(m * 1.02) + 16
+
+    def endpoints():
+        u = torch.rand(k, generator=g, device=device, dtype=torch.float64)
+        return (u.pow_(inv).mul_(n)).long().clamp_(max=n - 1)
+
+    a, b = endpoints(), endpoints()
+    keep = a != b
+    a, b = a[keep][:m], b[keep][:m]
+    perm = torch.randperm(n, generator=g, device=device)
+    return torch.stack([perm[a], perm[b]], dim=1).contiguous()
+
+
+def sample_test_nodes(n: int, T: int, sample_seed: int = 42) -> np.ndarray:
+    """'unbalanced' sampling: np.random.seed(sample_seed); np.random.choice(n, T, replace=False)
+    (attacker.py:45, utils/load.py:343-345, 379) — numpy's legacy stream, drawn on the host."""
+    rs = np.random.RandomState(sample_seed)
+    return rs.choice(np.arange(n), T, replace=False)
+
+
+def sample_test_nodes_typed(dataset: str, sample_type: str, indptr: np.ndarray, T: int, sample_seed: int = 42):
+    """construct_edge_sets_from_random_subgraph's node sampling (utils/load.py:338-379) for
+    unbalanced / unbalanced-lo / unbalanced-hi."""
+    n = len(indptr) - 1
+    if sample_type == "unbalanced":
+        cand = np.arange(n)
+    elif sample_type in ("unbalanced-lo", "unbalanced-hi"):
+        lo, hi = degree_thresholds(dataset)
+        deg = np.diff(indptr)
+        cand = np.where(deg <= lo)[0] if sample_type == "unbalanced-lo" else np.where(deg >= hi)[0]
+    else:
+        raise NotImplementedError(f"sample_type = {sample_type} not implemented!")
+    return np.random.RandomState(sample_seed).choice(cand, T, replace=False)   # same legacy stream as np.random.seed
+
+
+def degree_thresholds(dataset: str):
+    """utils/load.py:354-370."""
+    if dataset.startswith("twitch"):
+        return (10 if "PTBR" in dataset else 5), 10
+    if dataset in ("flickr", "ppi") or dataset.startswith("deezer"):
+        return 15, 30
+    if dataset in ("cora"):
+        return 3, 4
+    if dataset in ("citeseer"):
+        return 3, 3
+    if dataset in ("pubmed"):
+        return 10, 10
+    raise NotImplementedError(f"lo and hi for dataset = {dataset} not set!")
+
+

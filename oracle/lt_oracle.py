@@ -196,6 +196,99 @@ def influence_matrix(X, coo, weights, n, test_nodes, delta, dtype=torch.float64,
     return out
 
 
+class LocalInfluence:
+    """Float64 influence rows on graphs where two full forwards per row take minutes (config C5).
+
+    The reference's row for a perturbed node v is (f(X') − f(X))/δ read at the test nodes
+    (attacker.py:100-108, 220-229).  Every row of both forwards outside N̂(v) = {r : Â[r,v] ≠ 0} goes
+    through identical operations on identical inputs, so relu(H')−relu(H) is exactly 0 there and the
+    difference of the logits at u is Σ_{r ∈ N̂(u)∩N̂(v)} Â[u,r]·(relu(H'[r]) − relu(H[r]))·W2 (b2 cancels).
+    This class evaluates exactly that sub-problem in float64: H[r] for r ∈ N̂(v) from the FULL row r of Â
+    and the rows of X it touches, H'[r] = H[r] + Â[r,v]·(δ·x_v)·W1 (layers.py:31-34 on the perturbed row),
+    the ReLU difference taken by actual subtraction as the finite difference does (no case analysis),
+    then the layer-2 products over N̂(u)∩N̂(v).  It differs from two full float64 forwards only by float64
+    rounding of the cancelled terms (~1e-16·|logit|/δ ≈ 1e-11 absolute); tests/test_oracle_golden.py pins it
+    to `influence_matrix(dtype=float64)` and to the reference's own float64 run on every golden case.
+
+    `hits` (per row): hidden units (r,k) whose ReLU is within reach of the perturbation,
+    |H[r,k]| ≤ |δ·Â[r,v]|·max_k|P[v,k]| — the incidences the CUDA path sends through its exact fix-up."""
+
+    def __init__(self, indptr, indices, values, X, weights, test_nodes):
+        import scipy.sparse as sp
+        self.n = len(indptr) - 1
+        self.A = sp.csr_matrix((np.asarray(values, dtype=np.float64), np.asarray(indices), np.asarray(indptr)),
+                               shape=(self.n, self.n))
+        self.X = np.asarray(X)
+        self.w1, self.b1, self.w2 = [np.asarray(a, dtype=np.float64) for a in weights[:3]]
+        self.tn = np.asarray(test_nodes, dtype=np.int64)
+        self.AT = self.A[self.tn].tocsc()              # rows of Â at the test nodes, column-addressable
+
+    def row(self, v, delta, chunk_nnz=500_000):
+        """(influence [T] float64, structural 2-hop mask [T] bool, n_hits) for the perturbed node v."""
+        import scipy.sparse as sp
+        A = self.A
+        v = int(v)
+        R = A.indices[A.indptr[v]:A.indptr[v + 1]].astype(np.int64)          # pattern symmetric: N̂(v) = row v
+        sub = A[R]                                                          # full rows of N̂(v)
+        a_rv = np.asarray(sub[:, v].todense()).ravel()                      # Â[r,v], looked up in row r
+        H = np.empty((len(R), self.w1.shape[1]))
+        lens = np.diff(sub.indptr)
+        start = 0
+        while start < len(R):                                               # bounded temporaries on hub rows
+            stop = start + 1
+            acc = lens[start]
+            while stop < len(R) and acc + lens[stop] <= chunk_nnz:
+                acc += lens[stop]
+                stop += 1
+            part = sub[start:stop]
+            cols = np.unique(part.indices)
+            loc = sp.csr_matrix((part.data, np.searchsorted(cols, part.indices), part.indptr), shape=(stop - start, len(cols)))
+            H[start:stop] = (loc @ self.X[cols].astype(np.float64)) @ self.w1 + self.b1
+            start = stop
+        pv = self.X[v].astype(np.float64) @ self.w1
+        Hp = H + a_rv[:, None] * (delta * pv)[None, :]
+        dR = np.maximum(Hp, 0.0) - np.maximum(H, 0.0)
+        dQ = dR @ self.w2
+        B = self.AT[:, R]                                                   # [T, |R|]: Â[u,r] for test nodes u
+        dZ = B @ dQ
+        infl = np.sqrt((dZ * dZ).sum(axis=1)) / delta
+        mask = np.diff(B.tocsr().indptr) > 0
+        hits = int((np.abs(H) <= (np.abs(delta * a_rv) * np.abs(pv).max())[:, None]).any(axis=1).sum())
+        return infl, mask, hits
+
+    def rows(self, idx, delta):
+        out = np.zeros((len(idx), len(self.tn)))
+        mask = np.zeros((len(idx), len(self.tn)), dtype=bool)
+        hits = np.zeros(len(idx), dtype=np.int64)
+        for k, i in enumerate(idx):
+            out[k], mask[k], hits[k] = self.row(self.tn[i], delta)
+        return out, mask, hits
+
+
+def pick_parity_rows(indptr, test_nodes, n_hub=4, n_rand=12, seed=7):
+    """Rows for a bounded parity check: the `n_hub` highest-degree test nodes (longest incidence lists, multi-segment
+    SpMM rows, big F2 groups) plus `n_rand` seeded random ones.  Returns sorted unique indices into test_nodes."""
+    tn = np.asarray(test_nodes, dtype=np.int64)
+    deg = np.asarray(indptr)[tn + 1] - np.asarray(indptr)[tn]
+    hub = np.argsort(-deg, kind="stable")[:n_hub]
+    rnd = np.random.default_rng(seed).choice(len(tn), size=min(n_rand, len(tn)), replace=False)
+    return np.unique(np.concatenate([hub, rnd]))
+
+
+def compare_rows(got, ref):
+    """(support_equal, max relative error on the support) of influence rows against the float64 oracle."""
+    sup = ref != 0
+    same = bool(np.array_equal(got != 0, sup))
+    both = sup & (got != 0)
+    rel = float((np.abs(got[both] - ref[both]) / np.abs(ref[both])).max()) if both.any() else 0.0
+    return same, rel
+
+
+def influence_rows_local(indptr, indices, values, X, weights, test_nodes, rows, delta):
+    """Float64 influence rows `rows` (indices into test_nodes) by the 2-hop sub-problem — see LocalInfluence."""
+    return LocalInfluence(indptr, indices, values, X, weights, test_nodes).rows(list(rows), delta)[0]
+
+
 def k_hop_support(indptr, indices, test_nodes, hops):
     """Boolean [T,T]: test_nodes[j] within ``hops`` hops of test_nodes[i] in Â's pattern (a k-layer GCN's
     influence is bit-exactly 0 outside it: every forward touches the same zeros)."""

@@ -123,3 +123,28 @@ def test_a12_lapgraph(golden):
     ip, ix, dv, _ = O.lapgraph(g["a1_indptr"], g["a1_indices"], g["a1_data"], s.n, float(g["epsilon"]), 42)
     assert np.array_equal(ip, g["dp_indptr"]) and np.array_equal(ix, g["dp_indices"])
     assert np.array_equal(dv, g["dp_data"])
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_local_influence_oracle_pinned_to_the_reference_float64_run(golden, case):
+    """oracle.LocalInfluence (the 2-hop float64 sub-problem used where two full forwards per row take
+    minutes: config C5) equals the reference's own float64 run and the full-forward oracle: same exact-zero
+    support, values within 1e-6 relative (the only difference is float64 rounding of cancelled terms)."""
+    g = golden(case)
+    s, w = inputs(g)
+    ip, ix, val = O.coo_to_csr(g["a2_row"], g["a2_col"], g["a2_val"], s.n)
+    tn = g["a6_test_nodes"]
+    T = int(g["T"])
+    out, mask, _ = O.LocalInfluence(ip, ix, val, s.features, w, tn).rows(range(T), float(g["delta"]))
+    ref = g["a8_influence64"]
+    sup = ref != 0
+    assert np.array_equal(out != 0, sup)
+    assert (mask | ~sup).all()                       # structural 2-hop mask covers the support
+    assert (np.abs(out[sup] - ref[sup]) / np.abs(ref[sup])).max() <= 1e-6
+    full = O.influence_matrix(s.features, (g["a2_row"], g["a2_col"], g["a2_val"]), w, s.n, tn, float(g["delta"]),
+                              dtype=torch.float64, rows=range(0, T, 7))
+    sub = out[::7]
+    nz = full != 0
+    assert np.array_equal(sub != 0, nz)
+    assert (np.abs(sub[nz] - full[nz]) / np.abs(full[nz])).max() <= 1e-6
+    assert np.array_equal(O.influence_rows_local(ip, ix, val, s.features, w, tn, [0, 3], float(g["delta"])), out[[0, 3]])
