@@ -243,6 +243,18 @@ int lt_prof_enable(int on);
 int lt_prof_reset(void);
 int lt_prof_report(char* buf_host, int64_t cap);
 
+/* ---------------------------------------------------------------------------------------------
+ * Process-wide tuning / debugging switches.  The reference has no counterpart (its only knobs are main.py's argparse
+ * flags, main.py:17-93); these select between kernels that produce the same results and exist for tests and profiling.
+ * Initial values are read from the environment ONCE (LT_NO_OVERLAP, LT_NO_SIGN_PATH, LT_TC_WS, LT_SPMM_PANEL[_MB|_LMIN],
+ * LT_SPMM_HUB[_MB]); no compute call reads the environment.  Names: "overlap" (plan tail / big-group reduce on the
+ * library's side stream, default 1), "sign_path" (sign-mask form of H_R, 1), "tc_ws" (warp-specialised tcgen05 GEMM, 1),
+ * "spmm_panel" (column-panel SpMM, 0), "spmm_panel_mb" (48), "spmm_panel_lmin" (64), "spmm_hub" (hub-column L2 pinning
+ * in the restricted SpMM, 1), "spmm_hub_mb" (size of the pinned hub panel in MB, 64).
+ * ------------------------------------------------------------------------------------------- */
+int lt_set_option(const char* name_host, int value);
+int lt_get_option(const char* name_host, int* value_host);
+
 /* primitives exported for the unit tests */
 int lt_exclusive_scan_i32(const int32_t* in, int32_t* out /* n+1 */, int64_t n, lt_stream_t stream);
 int lt_radix_sort_pairs_u64(uint64_t* keys, uint64_t* vals /* nullable */, int64_t n, int begin_bit,

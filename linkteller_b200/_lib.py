@@ -55,6 +55,8 @@ _SIGS = {
     "lt_pair_gather": [P, I64, I32, I32, P, P, I64, P, P],
     "lt_dp_edgerand_apply": [P, P, P, I32, P, P, I64, P, P, P, I64, P, P],
     "lt_dp_lapgraph_select": [P, P, P, I32, P, I64, P, P, P, I64, P, P],
+    "lt_set_option": [C.c_char_p, INT],
+    "lt_get_option": [C.c_char_p, P],
     "lt_launch_count": [],
     "lt_prof_enable": [INT],
     "lt_prof_reset": [],

@@ -26,15 +26,20 @@ def slice_bounds(T: int, world: int, rank: int):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+def _world(group):
+    """(world, rank) of an EXPLICITLY passed process group; without one the call is single-rank even when
+    torch.distributed is initialised (a caller that attacks on one rank only must not hang in a collective)."""
+    if group is None:
+        return 1, 0
+    return torch.distributed.get_world_size(group), torch.distributed.get_rank(group)
+
+
 def influence_matrix(adj_hat: ops.DeviceCSR, x, w1, b1, w2, test_nodes: torch.Tensor, delta: float,
                      group=None, out: Optional[torch.Tensor] = None, want_info: bool = False):
     """[T,T] float32 influence matrix on the device; row i = perturb test_nodes[i], column j =
-    ‖Δlogits[test_nodes[j]]‖₂/δ.  With a process group, rows are sharded and all-gathered."""
+    ‖Δlogits[test_nodes[j]]‖₂/δ.  With a process group (passed explicitly), rows are sharded and all-gathered."""
     T = test_nodes.numel()
-    world, rank = 1, 0
-    if group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
-        world = torch.distributed.get_world_size(group)
-        rank = torch.distributed.get_rank(group)
+    world, rank = _world(group)
     if out is None:
         out = torch.empty((T, T), dtype=torch.float32, device=x.device)
     lo, hi = slice_bounds(T, world, rank)
@@ -52,10 +57,7 @@ def influence_matrix_model(adj_hat: ops.DeviceCSR, x, weights, test_nodes: torch
     """influence_matrix for the model the weights belong to: 4 tensors (w1,b1,w2,b2) → GCN, 6 → GCN3
     (--n-layer 3).  Same sharding: rank g owns a contiguous slice of the perturbed nodes."""
     T = test_nodes.numel()
-    world, rank = 1, 0
-    if group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
-        world = torch.distributed.get_world_size(group)
-        rank = torch.distributed.get_rank(group)
+    world, rank = _world(group)
     if out is None:
         out = torch.empty((T, T), dtype=torch.float32, device=x.device)
     lo, hi = slice_bounds(T, world, rank)

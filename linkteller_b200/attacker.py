@@ -350,6 +350,8 @@ class Attacker:
         (fpr, tpr, thresholds), (precision, recall, thresholds_2) = binary_clf_curves(
             thr.cpu().numpy(), tps.cpu().numpy(), fps.cpu().numpy())
         self.auc, self.ap = auc, ap
+        if self.group is not None and torch.distributed.get_rank(self.group) != 0:
+            return None                                  # sharded run: every rank holds the result, rank 0 reports and saves
         print('auc =', auc)
         print('ap =', ap)
 

@@ -78,6 +78,13 @@ struct Scratch {
 
 int device_alloc(void** out, size_t bytes, cudaStream_t s);
 
+// ---- process-wide options (lt_set_option / lt_get_option).  Initial values come from the environment ONCE, at the
+// first query (LT_NO_OVERLAP, LT_NO_SIGN_PATH, LT_TC_WS, LT_SPMM_PANEL, LT_SPMM_PANEL_MB, LT_SPMM_PANEL_LMIN,
+// LT_SPMM_HUB, LT_SPMM_HUB_MB); after that no call reads the environment.
+enum Opt { OPT_OVERLAP = 0, OPT_SIGN_PATH, OPT_TC_WS, OPT_SPMM_PANEL, OPT_SPMM_PANEL_MB, OPT_SPMM_PANEL_LMIN, OPT_SPMM_HUB,
+           OPT_SPMM_HUB_MB, OPT_COUNT };
+int opt(Opt which);
+
 // ---- phase timers (lt_prof_*): CUDA events on the launching stream, only when enabled ----
 struct ProfScope {
     int slot;

@@ -21,6 +21,8 @@
 
 #include <stdlib.h>
 
+#include <mutex>
+
 namespace lt {
 
 int gemm_f32(const float* A, int64_t lda, const int32_t* a_rows, const float* B, int64_t ldb, int transB,
@@ -641,8 +643,10 @@ static int plan_alloc(lt_plan* p, T** out, size_t count, cudaStream_t s) {
 // SpMM — which only needs the compacted frontier rows — already occupies the caller's stream.
 static cudaStream_t side_stream() {
     static cudaStream_t streams[64] = {};
+    static std::mutex mu;                       // two host threads may make their first call at the same time
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    std::lock_guard<std::mutex> lock(mu);
     if (!streams[dev]) {
         int lo_p = 0, hi_p = 0;
         cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p);
@@ -650,6 +654,10 @@ static cudaStream_t side_stream() {
     }
     return streams[dev];
 }
+
+// debugging switches (lt_set_option "overlap" / "sign_path"); the environment is read once per process, not per call
+static bool overlap_enabled() { return opt(OPT_OVERLAP) != 0; }
+static bool sign_path_enabled() { return opt(OPT_SIGN_PATH) != 0; }
 
 // joins the side stream back into the caller's stream on every exit path of plan_build
 struct StreamJoin {
@@ -946,10 +954,11 @@ static int frontier_reduce(const uint64_t* rec_key, const uint64_t* rec_val, con
     if (M == 0) return LT_OK;
     ProfScope prof2("frontier_reduce", s);
     // groups above F2_BIG records (a CTA each) write other output pairs than the small groups: they go first, on the
-    // side stream, and run next to the small-group kernel
+    // side stream, and run next to the small-group kernel.  The join is RAII: every exit path below (a failed launch
+    // included) makes the caller's stream wait for the side stream before the caller's scratch (dq, records) is freed.
     cudaStream_t side = s;
     if (M > F2_BIG) {
-        cudaStream_t sd = getenv("LT_NO_OVERLAP") ? nullptr : side_stream();
+        cudaStream_t sd = overlap_enabled() ? side_stream() : nullptr;
         if (sd) {
             cudaEvent_t ev;
             LT_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
@@ -959,6 +968,9 @@ static int frontier_reduce(const uint64_t* rec_key, const uint64_t* rec_val, con
             if (e2 != cudaSuccess) { set_error("frontier_reduce: fork failed: %s", cudaGetErrorString(e2)); return LT_ERR_CUDA; }
             side = sd;
         }
+    }
+    StreamJoin join(s, side);
+    if (M > F2_BIG) {
         k_frontier_reduce_big<<<(unsigned)num_sms() * 2, 32 * F2_BIG_WARPS, 0, side>>>(rec_key, rec_val, grp_off, big, n_big, dq, lddq,
                                                                                        c, out, ldo);
         LT_LAUNCH_CHECK();
@@ -975,14 +987,6 @@ static int frontier_reduce(const uint64_t* rec_key, const uint64_t* rec_val, con
     else LT_F2(32);
 #undef LT_F2
     LT_LAUNCH_CHECK();
-    if (side != s) {                                            // join: the big groups ran next to the small ones
-        cudaEvent_t ev;
-        LT_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-        cudaError_t e1 = cudaEventRecord(ev, side);
-        cudaError_t e2 = e1 == cudaSuccess ? cudaStreamWaitEvent(s, ev, 0) : e1;
-        cudaEventDestroy(ev);
-        if (e2 != cudaSuccess) { set_error("frontier_reduce: join failed: %s", cudaGetErrorString(e2)); return LT_ERR_CUDA; }
-    }
     return LT_OK;
 }
 
@@ -1422,7 +1426,7 @@ int attack_early(lt_plan* plan, void* vctx, cudaStream_t side) {
     // sign-mask path: H_R is never written — the GEMM keeps one bit per element and the row's smallest magnitude
     // (36 bytes per frontier row instead of 4h), F1 reads those, and the rows where a ReLU can switch are patched
     a.sign_path = aggregate_first && frontier_use_tc(plan->E, h, c) && h >= 16 && (int64_t)R * h * f >= ((int64_t)1 << 24) &&
-                  (uintptr_t)a.W1 % 16 == 0 && !getenv("LT_NO_SIGN_PATH");
+                  (uintptr_t)a.W1 % 16 == 0 && sign_path_enabled();
     if (aggregate_first) {
         // H_R = (Â[R,:]·X)·W1 + b1 : gathers f floats per non-zero instead of h
         LT_TRY(scratch.alloc(&a.AX, (size_t)R * f));
@@ -1469,7 +1473,9 @@ extern "C" int lt_attack_efficient(const int32_t* indptr, const int32_t* indices
     LT_CHECK_ARG(indptr && indices && values && test_nodes, "lt_attack_efficient: null pointer");
     LT_CHECK_ARG(X && W1 && b1 && W2 && out, "lt_attack_efficient: null pointer");
     LT_CHECK_ARG(f > 0 && h > 0 && c > 0 && ldx >= f && h % 4 == 0, "lt_attack_efficient: sizes (h % 4 == 0)");
-    LT_CHECK_ARG(n > 0 && T > 0 && lo >= 0 && hi >= lo && hi <= T, "lt_attack_efficient: need 0 <= lo <= hi <= T");
+    LT_CHECK_ARG(n > 0 && T > 0 && lo >= 0 && hi >= lo && hi <= T && ldo >= T,
+                 "lt_attack_efficient: need 0 <= lo <= hi <= T <= ldo");
+    LT_CHECK_ARG(delta != 0.f, "lt_attack_efficient: delta must not be 0");
     cudaStream_t s = (cudaStream_t)stream;
     if (hi == lo) return LT_OK;
     lt_plan* plan = new lt_plan();
@@ -1480,8 +1486,8 @@ extern "C" int lt_attack_efficient(const int32_t* indptr, const int32_t* indices
         AttackCtx a{indptr, indices, values, n, X, ldx, f, W1, b1, h, c, test_nodes, lo, s, &scratch};
         st = scratch.alloc(&a.Pt, (size_t)plan->Ts * h);
         if (st == LT_OK)
-            st = plan_build(plan, indptr, indices, values, test_nodes, s, getenv("LT_NO_OVERLAP") ? nullptr : attack_early, &a);
-        if (st == LT_OK && getenv("LT_NO_OVERLAP")) st = attack_early(plan, &a, s);
+            st = plan_build(plan, indptr, indices, values, test_nodes, s, overlap_enabled() ? attack_early : nullptr, &a);
+        if (st == LT_OK && !overlap_enabled()) st = attack_early(plan, &a, s);
         if (st == LT_OK) {
             if (a.sign_path) {
                 const int32_t lddq = frontier_lddq(plan->E, h, c);

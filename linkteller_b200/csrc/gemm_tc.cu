@@ -53,11 +53,8 @@ int tc_prepack_b(const float* B, int64_t ldb, int transB, int32_t N, int32_t K, 
     return LT_OK;
 }
 
-// LT_TC_WS=0 selects the lock-step kernel (k_gemm_tc) instead of the warp-specialised one (k_gemm_ws)
-bool tc_use_ws() {
-    const char* e = getenv("LT_TC_WS");
-    return !(e && e[0] == '0');
-}
+// option "tc_ws" = 0 (LT_TC_WS=0) selects the lock-step kernel (k_gemm_tc) instead of the warp-specialised one (k_gemm_ws)
+bool tc_use_ws() { return opt(OPT_TC_WS) != 0; }
 
 // handled = false ⇒ the caller uses the fp32 SIMT kernel (tiny problems are not worth a tensor-core launch)
 int gemm_3xtf32(const float* A, int64_t lda, const int32_t* a_rows, const float* B, int64_t ldb, int transB,

@@ -1,9 +1,40 @@
 // Library plumbing: thread-local error message, device info, GCN forward composed from the kernels.
 #include "common.cuh"
 
+#include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
+#include <mutex>
+
 namespace lt {
+
+// ---- options ----
+namespace {
+struct OptDef { const char* name; const char* env; int dflt; bool env_negates; };
+// env_negates: the variable being SET (to anything) switches the option off (LT_NO_*)
+const OptDef kOpts[OPT_COUNT] = {
+    {"overlap", "LT_NO_OVERLAP", 1, true},          {"sign_path", "LT_NO_SIGN_PATH", 1, true},
+    {"tc_ws", "LT_TC_WS", 1, false},                {"spmm_panel", "LT_SPMM_PANEL", 0, false},
+    {"spmm_panel_mb", "LT_SPMM_PANEL_MB", 48, false}, {"spmm_panel_lmin", "LT_SPMM_PANEL_LMIN", 64, false},
+    {"spmm_hub", "LT_SPMM_HUB", 1, false},          {"spmm_hub_mb", "LT_SPMM_HUB_MB", 64, false},
+};
+std::atomic<int> g_opt[OPT_COUNT];
+std::once_flag g_opt_once;
+void opt_init() {
+    for (int i = 0; i < OPT_COUNT; ++i) {
+        int v = kOpts[i].dflt;
+        const char* e = getenv(kOpts[i].env);
+        if (e) v = kOpts[i].env_negates ? 0 : atoi(e);
+        g_opt[i].store(v);
+    }
+}
+}  // namespace
+
+int opt(Opt which) {
+    std::call_once(g_opt_once, opt_init);
+    return g_opt[which].load(std::memory_order_relaxed);
+}
 
 static thread_local char g_err[1024] = "";
 long long g_launches = 0;
@@ -77,6 +108,22 @@ extern "C" int lt_device_info(int* sm_count_host, int* cc_major_host, int* cc_mi
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
     }
     return LT_OK;
+}
+
+extern "C" int lt_set_option(const char* name, int value) {
+    LT_CHECK_ARG(name, "lt_set_option: null name");
+    std::call_once(g_opt_once, opt_init);
+    for (int i = 0; i < OPT_COUNT; ++i)
+        if (strcmp(kOpts[i].name, name) == 0) { g_opt[i].store(value); return LT_OK; }
+    set_error("lt_set_option: unknown option '%s'", name);
+    return LT_ERR_ARG;
+}
+extern "C" int lt_get_option(const char* name, int* value_host) {
+    LT_CHECK_ARG(name && value_host, "lt_get_option: null pointer");
+    for (int i = 0; i < OPT_COUNT; ++i)
+        if (strcmp(kOpts[i].name, name) == 0) { *value_host = opt((Opt)i); return LT_OK; }
+    set_error("lt_get_option: unknown option '%s'", name);
+    return LT_ERR_ARG;
 }
 
 extern "C" int64_t lt_launch_count(void) { return (int64_t)g_launches; }

@@ -469,11 +469,9 @@ int spmm_csr_f32_seg(const int32_t* indptr, const int32_t* indices, const float*
     // dense operand far beyond the L2 and enough rows to amortise the extra launches: long rows go through
     // one launch per column panel, short rows (a piece per panel would be a couple of non-zeros) stay plain
     const int64_t b_bytes = (int64_t)n_cols * d * 4;
-    const char* pm = getenv("LT_SPMM_PANEL_MB");
-    const char* pl = getenv("LT_SPMM_PANEL_LMIN");
-    const int64_t panel_bytes = (int64_t)(pm ? atoi(pm) : 48) << 20;
-    const int32_t lmin = pl ? atoi(pl) : 64;
-    const bool use_panel = d4 <= 32 && b_bytes >= ((int64_t)256 << 20) && n_rows >= 32768 && getenv("LT_SPMM_PANEL");
+    const int64_t panel_bytes = (int64_t)opt(OPT_SPMM_PANEL_MB) << 20;
+    const int32_t lmin = opt(OPT_SPMM_PANEL_LMIN);
+    const bool use_panel = d4 <= 32 && b_bytes >= ((int64_t)256 << 20) && n_rows >= 32768 && opt(OPT_SPMM_PANEL) != 0;
     if (!use_panel) {
         if (seg_off_known && total_seg_known >= 0) return plain_pass(nullptr, n_rows, seg_off_known, total_seg_known);
         int32_t* seg_off;

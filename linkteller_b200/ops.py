@@ -60,6 +60,33 @@ def launch_count() -> int:
     return int(_lib.load().lt_launch_count())
 
 
+def set_option(name: str, value: int) -> None:
+    """Process-wide kernel-selection switch (lt_set_option): "overlap", "sign_path", "tc_ws", "spmm_panel", …"""
+    _lib.check(_lib.load().lt_set_option(name.encode(), int(value)), "lt_set_option")
+
+
+def get_option(name: str) -> int:
+    v = C.c_int()
+    _lib.check(_lib.load().lt_get_option(name.encode(), C.byref(v)), "lt_get_option")
+    return v.value
+
+
+class option:
+    """`with ops.option("sign_path", 0): …` — set a switch and restore it afterwards."""
+
+    def __init__(self, name: str, value: int):
+        self.name, self.value = name, value
+
+    def __enter__(self):
+        self.old = get_option(self.name)
+        set_option(self.name, self.value)
+        return self
+
+    def __exit__(self, *exc):
+        set_option(self.name, self.old)
+        return False
+
+
 class profile:
     """Context manager around the library's phase timers: `with ops.profile() as p: ...; p.report()`
     → {phase: (launch groups, total ms)} measured with CUDA events on the launching stream."""
@@ -566,6 +593,7 @@ def pair_influence(adj: DeviceCSR, x, w1, b1, w2, perturbed: torch.Tensor, obser
         return out[:0]
     if int(torch.minimum(perturbed.min(), observed.min())) < 0 or int(torch.maximum(perturbed.max(), observed.max())) >= n:
         raise IndexError("pair node outside the graph")
+    w1, b1, w2 = _pad_first_hidden(w1, b1, w2)
     all_nodes = torch.arange(n, dtype=torch.int32, device=x.device)
     need = torch.zeros(n, dtype=torch.bool, device=x.device)
     need[perturbed.long()] = True

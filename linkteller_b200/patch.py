@@ -138,6 +138,7 @@ def install(reference_path=None, patch_layers=True, patch_normalization=True, pa
                                       getattr(a, "noise_type", "laplace"), getattr(a, "delta", 1e-5))
                 m = out.to_scipy()
                 if perturb_type != "discrete":
+                    self.n_nodes = adj.shape[0]       # side effect of perturb_adj_continuous (worker.py:282)
                     m = m.astype("int32")             # worker.py:331: np.ones(..., dtype=np.int32)
                 return m
 

@@ -296,11 +296,160 @@ def run_case_gcn3(name, shape, seed, h1, h2, T, **override):
           f"{os.path.getsize(path) / 1024:.0f} KiB")
 
 
+def _ref_problem(shape, seed, hidden, dp=None, epsilon=5.0, noise_seed=42, norm="FirstOrderGCN", **override):
+    """Synthetic inputs of a named shape pushed through the reference's own load path: graph_reader →
+    (perturb_adj) → fetch_normalization → sparse_mx_to_torch_sparse_tensor (worker.py:631-645)."""
+    s = synth.make(shape, seed=seed, hidden=hidden, **override)
+    adj_ori = ref_graph_reader(s.edges, s.n, "twitch/ES/RU").tocsr()
+    adj_ori.sort_indices()
+    adj_model, noisy = adj_ori, None
+    if dp:
+        w = ref_worker.Worker.__new__(ref_worker.Worker)
+        w.args = types.SimpleNamespace(epsilon=epsilon, noise_seed=noise_seed, noise_type="laplace", delta=1e-5)
+        if not hasattr(np, "bool"):
+            np.bool = bool
+        noisy = quiet(w.perturb_adj, adj_ori.copy(), dp).tocsr()
+        noisy.sort_indices()
+        adj_model = noisy
+    coo = ref_utils.fetch_normalization(norm)(adj_model)
+    adj_t = quiet(ref_utils.sparse_mx_to_torch_sparse_tensor, coo)
+    return s, adj_ori, noisy, adj_t
+
+
+def _ref_attack(s, adj_ori, adj_t, weights, hidden, args, dbl, save_dir=None):
+    """One run of the reference's link_prediction_attack_efficient (attacker.py:209-247).  With save_dir the real
+    compute_and_save writes its .pt there; otherwise the pair scores are captured.  Returns a dict."""
+    model = build_model(s.f, hidden, s.c, weights, double=dbl)
+    X = torch.from_numpy(s.features)
+    feats = X.double() if dbl else X
+    adj = adj_t.double() if dbl else adj_t
+    wk = types.SimpleNamespace(n_nodes=s.n, n_features=s.f, features=feats, adj_full=adj, features_2=feats, adj_2=adj,
+                               adj_ori=adj_ori)
+    att = ref_attacker.Attacker(args, model, wk)
+    quiet(att.prepare_test_data)
+    res = dict(test_nodes=np.asarray(att.test_nodes), n_exist=len(att.exist_edges))
+    if save_dir is None:
+        cap = {}
+        att.compute_and_save = lambda e, ne: cap.update(e=np.asarray(e), ne=np.asarray(ne))
+        quiet(att.link_prediction_attack_efficient)
+        res.update(exist=cap["e"], nonexist=cap["ne"])
+    else:
+        cwd = os.getcwd()
+        os.chdir(save_dir)
+        try:
+            buf = io.StringIO()
+            with contextlib.redirect_stdout(buf), contextlib.redirect_stderr(io.StringIO()):
+                att.link_prediction_attack_efficient()
+        finally:
+            os.chdir(cwd)
+        lines = buf.getvalue().splitlines()
+        res["auc"] = float([l for l in lines if l.startswith("auc =")][0].split("=")[1])
+        res["ap"] = float([l for l in lines if l.startswith("ap =")][0].split("=")[1])
+        res["saved_to"] = [l for l in lines if l.startswith("attack results saved to")][0].split(": ")[1]
+    return res
+
+
+def run_case_config(name, shape, hidden, T, dp=None, epsilon=5.0, noise_seed=42, sample_type="unbalanced",
+                    dataset="twitch/ES/RU"):
+    """A BASELINE.json configuration at FULL size through the unmodified reference: C1 (twitch-RU shape, hidden 256,
+    T = 500, --attack-mode efficient) and C4 (the same through Lapgraph / EdgeRand ε = 5, pairs labelled from the
+    clean graph).  Stores the reference's pair scores as shipped (float32 arithmetic) and with model.double(), and
+    the AUC / AP its own compute_and_save prints (attacker.py:378-386)."""
+    from sklearn import metrics
+    import time as _t
+    t0 = _t.time()
+    s, adj_ori, noisy, adj_t = _ref_problem(shape, 0, hidden, dp, epsilon, noise_seed)
+    weights = synth.gcn_weights(s.f, hidden, s.c, seed=42)
+    mode = "vanilla" if dp else "vanilla-clean"
+    args = types.SimpleNamespace(dataset=dataset, sample_type=sample_type, n_test=T, influence=1e-4, sample_seed=42,
+                                 mode=mode, attack_mode="efficient", perturb_type=dp, epsilon=epsilon, noise_seed=noise_seed)
+    out = dict(shape=shape, seed=0, hidden=hidden, T=T, delta=1e-4, sample_seed=42, dp=dp or "", epsilon=epsilon,
+               noise_seed=noise_seed, sample_type=sample_type, dataset=dataset, norm="FirstOrderGCN")
+    if dp:
+        out.update(dp_indptr=noisy.indptr, dp_indices=noisy.indices, dp_data=noisy.data)
+    ind = adj_t._indices().numpy()
+    out.update(hat_nnz=ind.shape[1], hat_val_sum=float(adj_t._values().double().sum()))
+    with tempfile.TemporaryDirectory() as td:
+        r32 = _ref_attack(s, adj_ori, adj_t, weights, hidden, args, dbl=False, save_dir=td)
+        saved = torch.load(os.path.join(td, r32["saved_to"]), weights_only=False)
+    y = np.asarray(saved["result"]["y"])
+    pred32 = np.asarray(saved["result"]["pred"])
+    assert np.array_equal(pred32, pred32.astype(np.float32).astype(np.float64))      # float32-computed norms
+    out.update(test_nodes=r32["test_nodes"], y=np.packbits(y.astype(np.uint8)), n_pairs=len(y), n_exist=int(y.sum()),
+               pred32=pred32.astype(np.float32), auc32=r32["auc"], ap32=r32["ap"], filename=r32["saved_to"])
+    r64 = _ref_attack(s, adj_ori, adj_t, weights, hidden, args, dbl=True)
+    pred64 = np.r_[r64["exist"], r64["nonexist"]]
+    fpr, tpr, _ = metrics.roc_curve(y, pred64)
+    out.update(pred64=pred64, auc64=float(metrics.auc(fpr, tpr)), ap64=float(metrics.average_precision_score(y, pred64)))
+    path = os.path.join(HERE, f"{name}.npz")
+    np.savez_compressed(path, **out)
+    print(f"{name}: T={T} pairs={len(y)} edges={int(y.sum())} auc32={out['auc32']:.6f} auc64={out['auc64']:.6f} "
+          f"ap32={out['ap32']:.6f} ap64={out['ap64']:.6f} [{_t.time() - t0:.0f} s] → {os.path.getsize(path) / 1024:.0f} KiB")
+
+
+def run_case_stats(name, shape="twitch", hidden=64, T=300, dp="discrete", epsilon=5.0, m=12000):
+    """attack_stats_all.py (the offline ranking, :47-74, 86-116) run UNMODIFIED on nine result files the reference's own
+    compute_and_save wrote (3 sample types x 3 sample seeds, DP file-name pattern — the one the script has active).
+    The script's xlsx export needs openpyxl (absent) and is outside the hot path: it is executed up to that point and
+    its result arrays are read from its namespace."""
+    # a sparser graph than C1 (m undirected edges) so that ≥ T nodes have degree ≤ 5 and every cell has edges: with no edge
+    # in a cell the script's get_closest(0) never terminates (attack_stats_all.py:56-58)
+    s, adj_ori, noisy, adj_t = _ref_problem(shape, 0, hidden, dp, epsilon, 42, m=m)
+    weights = synth.gcn_weights(s.f, hidden, s.c, seed=42)
+    out = dict(shape=shape, hidden=hidden, T=T, dp=dp, epsilon=epsilon, dataset="twitch/ES/RU", m=m)
+    sample_types = ["unbalanced-lo", "unbalanced", "unbalanced-hi"]
+    seeds = [42, 2, 82]
+    with tempfile.TemporaryDirectory() as td:
+        for st in sample_types:
+            for sd in seeds:
+                args = types.SimpleNamespace(dataset="twitch/ES/RU", sample_type=st, n_test=T, influence=1e-4, sample_seed=sd,
+                                             mode="vanilla", attack_mode="efficient", perturb_type=dp, epsilon=epsilon,
+                                             noise_seed=42)
+                r = _ref_attack(s, adj_ori, adj_t, weights, hidden, args, dbl=False, save_dir=td)
+                saved = torch.load(os.path.join(td, r["saved_to"]), weights_only=False)
+                out[f"y_{st}_{sd}"] = np.packbits(np.asarray(saved["result"]["y"], dtype=np.uint8))
+                out[f"pred_{st}_{sd}"] = np.asarray(saved["result"]["pred"]).astype(np.float32)
+                out[f"file_{st}_{sd}"] = r["saved_to"]
+        src = open(os.path.join(REF, "attack_stats_all.py")).read()
+        ns = {"__name__": "__main__"}
+        cwd, argv = os.getcwd(), sys.argv
+        os.chdir(td)
+        sys.argv = ["attack_stats_all.py", "--dataset", "twitch/ES/RU", "--method-type", "efficient", "--perturb-type", dp,
+                    "--n-attack", str(T), "--eps", str(epsilon)]
+        _load = torch.load
+        torch.load = lambda f, *a, **k: _load(f, *a, weights_only=False, **k)      # torch ≥ 2.6 default; data is ours
+        try:
+            with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
+                try:
+                    exec(compile(src, "attack_stats_all.py", "exec"), ns)
+                except (ImportError, ModuleNotFoundError, ValueError) as e:                       # pd.ExcelWriter(engine='openpyxl')
+                    out["stopped_at"] = repr(e)[:200]
+        finally:
+            os.chdir(cwd)
+            sys.argv = argv
+            torch.load = _load
+    for k in ("n_edges", "approx", "expn", "result_prec", "result_rec", "result_cnt", "result_f1", "result_auc"):
+        out[k] = np.asarray(ns[k])
+    out["n_pairs"] = T * (T - 1) // 2
+    path = os.path.join(HERE, f"{name}.npz")
+    np.savez_compressed(path, **out)
+    print(f"{name}: n_edges={out['n_edges'].tolist()} approx={out['approx'].tolist()} expn={out['expn'].tolist()} "
+          f"auc={np.round(out['result_auc'], 4).tolist()} stopped_at={out.get('stopped_at')} → {os.path.getsize(path) / 1024:.0f} KiB")
+
+
 if __name__ == "__main__":
     torch.set_num_threads(4)
     if "--gcn3-only" in sys.argv:
         run_case_gcn3("tiny_gcn3", "tiny", seed=6, h1=32, h2=16, T=40)
         run_case_gcn3("sparse_gcn3", "small", seed=7, h1=32, h2=24, T=120, m=1800)
+        sys.exit(0)
+    if "--configs-only" in sys.argv:
+        run_case_config("c1_twitch", "twitch", hidden=256, T=500)
+        run_case_config("c4_twitch_edgerand", "twitch", hidden=256, T=500, dp="discrete")
+        run_case_config("c4_twitch_lapgraph", "twitch", hidden=256, T=500, dp="continuous")
+        sys.exit(0)
+    if "--stats-only" in sys.argv:
+        run_case_stats("stats_twitch")
         sys.exit(0)
     if "--next-only" in sys.argv:
         run_case_next("tiny_next", "tiny", seed=5, hidden=32)
@@ -318,3 +467,7 @@ if __name__ == "__main__":
     run_case_next("tiny_next", "tiny", seed=5, hidden=32)
     run_case_gcn3("tiny_gcn3", "tiny", seed=6, h1=32, h2=16, T=40)
     run_case_gcn3("sparse_gcn3", "small", seed=7, h1=32, h2=24, T=120, m=1800)
+    run_case_config("c1_twitch", "twitch", hidden=256, T=500)
+    run_case_config("c4_twitch_edgerand", "twitch", hidden=256, T=500, dp="discrete")
+    run_case_config("c4_twitch_lapgraph", "twitch", hidden=256, T=500, dp="continuous")
+    run_case_stats("stats_twitch")

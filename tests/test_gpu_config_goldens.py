@@ -1,0 +1,68 @@
+"""BASELINE.json configurations C1 and C4 at FULL size against the unmodified reference's own run
+(tests/golden/c1_twitch.npz, c4_twitch_{edgerand,lapgraph}.npz from tests/golden/make_golden.py --configs-only):
+twitch-RU shape (n = 4385, 37 304 edges, f = 3170, hidden 256), --attack-mode efficient, T = 500, δ = 1e-4;
+C4 = the same model queried on the Lapgraph / EdgeRand (ε = 5) graph with pairs labelled from the clean graph.
+The whole chain runs through the reference-facing classes (Attacker on a duck-typed worker): sampling, pair
+labels, DP perturbation, normalisation, influence matrix, pair scores, AUC / AP, the saved .pt."""
+import types
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import torch
+
+from linkteller_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("case", ["c1_twitch", "c4_twitch_edgerand", "c4_twitch_lapgraph"])
+def test_full_size_config_matches_the_reference_run(golden, case, tmp_path, monkeypatch):
+    from linkteller_b200 import adj as A, dp as DP, gcn, ops
+    from linkteller_b200.attacker import Attacker
+    g = golden(case)
+    hidden, T, dp = int(g["hidden"]), int(g["T"]), str(g["dp"])
+    s = synth.make(str(g["shape"]), seed=int(g["seed"]), hidden=hidden)
+    w = synth.gcn_weights(s.f, hidden, s.c, seed=42)
+    clean = A.adj_from_edges(s.edges, s.n)                                   # graph_reader (load.py:452-460)
+    adj_ori = clean.to_scipy()
+    model_adj = clean
+    if dp:                                                                   # Worker.perturb_adj (worker.py:206-335)
+        model_adj = DP.perturb_adj(clean, dp, float(g["epsilon"]), int(g["noise_seed"]))
+        noisy = model_adj.to_scipy()
+        assert np.array_equal(noisy.indptr, g["dp_indptr"]) and np.array_equal(noisy.indices, g["dp_indices"])
+        assert np.array_equal(noisy.data, g["dp_data"].astype(noisy.data.dtype))
+    hat = ops.normalize_adj(model_adj, str(g["norm"]))
+    assert hat.nnz == int(g["hat_nnz"])
+    assert abs(float(hat.values.double().sum()) - float(g["hat_val_sum"])) <= 1e-9 * float(g["hat_val_sum"])
+    model = gcn.GCN(s.f, hidden, s.c, 0.5)
+    model.load_state_dict({k: torch.from_numpy(a) for k, a in zip(("gc1.weight", "gc1.bias", "gc2.weight", "gc2.bias"), w)})
+    model = model.cuda().eval()
+    feats = torch.from_numpy(s.features).cuda()
+    worker = types.SimpleNamespace(n_nodes=s.n, n_features=s.f, features=feats, adj_full=hat, features_2=feats, adj_2=hat,
+                                   adj_ori=adj_ori)
+    args = types.SimpleNamespace(dataset=str(g["dataset"]), sample_type=str(g["sample_type"]), n_test=T, influence=1e-4,
+                                 sample_seed=42, mode="vanilla" if dp else "vanilla-clean", attack_mode="efficient",
+                                 perturb_type=dp or None, epsilon=float(g["epsilon"]), noise_seed=int(g["noise_seed"]))
+    monkeypatch.chdir(tmp_path)
+    att = Attacker(args, model, worker)
+    att.prepare_test_data()
+    assert np.array_equal(att.test_nodes, g["test_nodes"])
+    att.link_prediction_attack_efficient()
+    saved = torch.load(str(g["filename"]), weights_only=False)               # the reference's own file name
+    y = np.asarray(saved["result"]["y"])
+    pred = np.asarray(saved["result"]["pred"])
+    n_pairs = int(g["n_pairs"])
+    assert np.array_equal(y, np.unpackbits(g["y"])[:n_pairs]) and int(y.sum()) == int(g["n_exist"])
+    p32, p64 = g["pred32"].astype(np.float64), g["pred64"]
+    assert np.array_equal(pred == 0, p64 == 0) and np.array_equal(pred == 0, p32 == 0)     # exact zeros, all 124 750 pairs
+    nz = p64 != 0
+    rel = np.abs(pred[nz] - p64[nz]) / np.abs(p64[nz])
+    rel32 = np.abs(p32[nz] - p64[nz]) / np.abs(p64[nz])
+    assert rel.max() <= 1e-3, rel.max()                                      # north_star tolerance, vs the float64 run
+    assert rel.max() <= rel32.max() and np.median(rel) <= np.median(rel32)   # closer to it than the reference as shipped
+    # north_star: "matching edge-recovery AUC on the twitch-RU-shaped config"
+    assert abs(att.auc - float(g["auc64"])) <= 1e-6, (att.auc, float(g["auc64"]))
+    assert abs(att.ap - float(g["ap64"])) <= 1e-5, (att.ap, float(g["ap64"]))
+    d32 = abs(float(g["auc32"]) - float(g["auc64"]))                         # the reference's own float32 noise
+    assert abs(att.auc - float(g["auc32"])) <= d32 + 1e-6

@@ -63,15 +63,13 @@ def test_sign_mask_path_matches_value_path_and_oracle(monkeypatch):
     from linkteller_b200 import ops, workloads
     for delta, min_exact in ((1e-4, 0), (3e-2, 100)):
         wl = workloads.make("ppi", delta=delta, f=52)       # f % 4 == 0 and f < h: aggregate-first precompute
-        monkeypatch.delenv("LT_NO_SIGN_PATH", raising=False)
-        with ops.profile() as prof:
+        with ops.option("sign_path", 1), ops.profile() as prof:
             a, info = ops.attack_efficient(wl.adj_hat, wl.x, wl.w1, wl.b1, wl.w2, wl.test_nodes, wl.delta, want_info=True)
         assert "gemm_h" in prof.report() and "frontier_dq" in prof.report()
         assert info["exact_path_incidences"] >= min_exact
-        monkeypatch.setenv("LT_NO_SIGN_PATH", "1")
-        b, info_b = ops.attack_efficient(wl.adj_hat, wl.x, wl.w1, wl.b1, wl.w2, wl.test_nodes, wl.delta, want_info=True)
+        with ops.option("sign_path", 0):
+            b, info_b = ops.attack_efficient(wl.adj_hat, wl.x, wl.w1, wl.b1, wl.w2, wl.test_nodes, wl.delta, want_info=True)
         assert info_b["exact_path_incidences"] == 0
-        monkeypatch.delenv("LT_NO_SIGN_PATH")
         a, b = a.cpu().numpy(), b.cpu().numpy()
         assert np.array_equal(a == 0, b == 0)
         nz = b != 0

@@ -40,31 +40,29 @@ def test_gemm_3xtf32_matches_float64(M, N, K):
 
 @pytest.mark.parametrize("M,N,K", [(300, 256, 100), (20000, 48, 256), (513, 121, 40)])
 def test_lockstep_and_warp_specialised_kernels_agree(M, N, K, monkeypatch):
-    """k_gemm_ws (default) and k_gemm_tc (LT_TC_WS=0) stage the same operands and issue the same MMAs in the same
+    """k_gemm_ws (default) and k_gemm_tc (option tc_ws = 0) stage the same operands and issue the same MMAs in the same
     order per accumulator: the results are bit-identical."""
     from linkteller_b200 import ops
     rng = np.random.default_rng(M + N + K)
     a = dev(rng.standard_normal((M, K), dtype=np.float32))
     b = dev(rng.standard_normal((K, N), dtype=np.float32))
     bias = dev(rng.standard_normal(N, dtype=np.float32))
-    monkeypatch.delenv("LT_TC_WS", raising=False)
-    ws = ops.gemm(a, b, bias=bias, relu=True, algo=2)
-    monkeypatch.setenv("LT_TC_WS", "0")
-    ls = ops.gemm(a, b, bias=bias, relu=True, algo=2)
-    monkeypatch.delenv("LT_TC_WS")
+    with ops.option("tc_ws", 1):
+        ws = ops.gemm(a, b, bias=bias, relu=True, algo=2)
+    with ops.option("tc_ws", 0):
+        ls = ops.gemm(a, b, bias=bias, relu=True, algo=2)
     assert torch.equal(ws, ls)
 
 
 def test_attack_paths_agree_without_overlap(monkeypatch):
-    """LT_NO_OVERLAP=1 (everything on the caller's stream) and the default (plan tail and big-group reduce on the side
+    """option overlap = 0 (everything on the caller's stream) and the default (plan tail and big-group reduce on the side
     stream) run the same kernels on the same data: identical influence rows."""
     from linkteller_b200 import ops, workloads
     wl = workloads.make("ppi", f=52)
-    monkeypatch.delenv("LT_NO_OVERLAP", raising=False)
-    a = ops.attack_efficient(wl.adj_hat, wl.x, wl.w1, wl.b1, wl.w2, wl.test_nodes, wl.delta)
-    monkeypatch.setenv("LT_NO_OVERLAP", "1")
-    b = ops.attack_efficient(wl.adj_hat, wl.x, wl.w1, wl.b1, wl.w2, wl.test_nodes, wl.delta)
-    monkeypatch.delenv("LT_NO_OVERLAP")
+    with ops.option("overlap", 1):
+        a = ops.attack_efficient(wl.adj_hat, wl.x, wl.w1, wl.b1, wl.w2, wl.test_nodes, wl.delta)
+    with ops.option("overlap", 0):
+        b = ops.attack_efficient(wl.adj_hat, wl.x, wl.w1, wl.b1, wl.w2, wl.test_nodes, wl.delta)
     assert torch.equal(a, b)
     for _ in range(3):                                  # and it is repeatable (no race between the streams)
         assert torch.equal(a, ops.attack_efficient(wl.adj_hat, wl.x, wl.w1, wl.b1, wl.w2, wl.test_nodes, wl.delta))

@@ -26,18 +26,12 @@ def test_spmm_panel_matches_plain_and_float64():
     assert deg > 256                             # hub rows span several segments
     out0 = ops.spmm(hat, b, bias=bias, relu=True)     # plain kernel (default)
     sub0 = ops.spmm(hat, b, rows=rows)
-    os.environ["LT_SPMM_PANEL"] = "1"                # the panel path is opt-in
-    try:
+    with ops.option("spmm_panel", 1):                # the panel path is opt-in
         out = ops.spmm(hat, b, bias=bias, relu=True)
         sub = ops.spmm(hat, b, rows=rows)
-        for mb, lmin in (("16", "1"), ("100", "64"), ("48", "300")):
-            os.environ["LT_SPMM_PANEL_MB"], os.environ["LT_SPMM_PANEL_LMIN"] = mb, lmin
-            try:
+        for mb, lmin in ((16, 1), (100, 64), (48, 300)):
+            with ops.option("spmm_panel_mb", mb), ops.option("spmm_panel_lmin", lmin):
                 assert torch.equal(ops.spmm(hat, b, rows=rows), sub0)
-            finally:
-                del os.environ["LT_SPMM_PANEL_MB"], os.environ["LT_SPMM_PANEL_LMIN"]
-    finally:
-        del os.environ["LT_SPMM_PANEL"]
     # float64 check through torch's CSR product
     A = torch.sparse_csr_tensor(hat.indptr.long(), hat.indices.long(), hat.values.double(), (n, n))
     ref = torch.relu(A @ b.double() + bias.double())

@@ -155,7 +155,10 @@ def _model_worker(rank, world, T, n_weights, port, ok):
         return out
     ops.attack_rows = fake_rows
     tn = torch.arange(T, dtype=torch.int32)
-    got = attack.influence_matrix_model(None, torch.zeros(1), [torch.zeros(1)] * n_weights, tn, 1e-4)
+    got = attack.influence_matrix_model(None, torch.zeros(1), [torch.zeros(1)] * n_weights, tn, 1e-4, group=dist.group.WORLD)
+    alone = attack.influence_matrix_model(None, torch.zeros(1), [torch.zeros(1)] * n_weights, tn, 1e-4)   # no group: no sharding, no collective
+    assert torch.equal(alone, full) and calls[-1] == (0, T)
+    calls.pop()
     ok[rank] = int(torch.equal(got, full) and calls == [attack.slice_bounds(T, world, rank)])
     dist.destroy_process_group()
 
@@ -182,3 +185,18 @@ def test_profile_summary_tool_reads_the_committed_launch_list():
     share = float(lines[0].split()[-1].rstrip("%"))
     assert 50.0 < share < 90.0
     assert any(ln.startswith("lt::k_gemm_ws") for ln in lines) and any(ln.startswith("lt::k_scan_lookback") for ln in lines)
+
+
+def test_density_rounding_follows_get_closest():
+    """attack_stats_all.py:56-65 — one significant digit, mantissa rounded half up; :87-88 the five ratios."""
+    from linkteller_b200 import stats
+    assert stats.get_closest(0.0034) == (3, 3)
+    assert stats.get_closest(0.0035) == (4, 3) or stats.get_closest(0.0035) == (3, 3)     # 3.5000000000000004 vs 3.4999…
+    assert stats.get_closest(0.00096) == (10, 4)          # upstream quirk: the mantissa may round up to 10
+    assert stats.get_closest(0.5) == (5, 1)
+    a, b, ratios = stats.density_ratios(43)               # 43 / 124750 = 3.4e-4
+    assert (a, b) == (3, 4) and np.allclose(ratios, [7.5e-5, 1.5e-4, 3e-4, 6e-4, 1.2e-3])
+    assert stats.calc_f1(0, 1) == 0 and abs(stats.calc_f1(0.5, 1.0) - 2 / 3) < 1e-15
+    with pytest.raises(ValueError):
+        stats.get_closest(0.0)
+    assert stats.result_filename("ppi", "efficient", "unbalanced", 500, 42) == "eval_ppi/efficient_unbalanced_500_42.pt"
