@@ -53,6 +53,8 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--ref-budget", type=float, default=330.0, help="wall-clock cap of the reference arm's probe + warm-up + timed steps (s)")
     ap.add_argument("--no-parity", action="store_true", help="skip the parity_check / cpu_baseline legs")
+    ap.add_argument("--opt", action="append", default=[], metavar="NAME=VALUE",
+                    help="library switch for experiments (lt_set_option), e.g. --opt spmm_hub=0; recorded on the line")
     return ap.parse_args()
 
 
@@ -266,6 +268,9 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     ops.device_info()
+    for kv in args.opt:
+        name, val = kv.split("=")
+        ops.set_option(name, int(val))
 
     wl = workloads.make(args.workload, device=dev, n_test=args.n_test)
     T = wl.T
@@ -434,7 +439,7 @@ def main():
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": bench_config(wl.describe(), world),
-            "l2_flush_between_steps": bool(flush),
+            "l2_flush_between_steps": bool(flush), "options": list(args.opt),
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline, "roofline_frontier": roofline_frontier,
             "phases_ms_per_step": {k: round(v, 4) for k, v in per_step.items()},

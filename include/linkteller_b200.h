@@ -250,7 +250,10 @@ int lt_prof_report(char* buf_host, int64_t cap);
  * LT_SPMM_HUB[_MB]); no compute call reads the environment.  Names: "overlap" (plan tail / big-group reduce on the
  * library's side stream, default 1), "sign_path" (sign-mask form of H_R, 1), "tc_ws" (warp-specialised tcgen05 GEMM, 1),
  * "spmm_panel" (column-panel SpMM, 0), "spmm_panel_mb" (48), "spmm_panel_lmin" (64), "spmm_hub" (hub-column L2 pinning
- * in the restricted SpMM, 1), "spmm_hub_mb" (size of the pinned hub panel in MB, 64).
+ * in the restricted SpMM, 0), "spmm_hub_mb" (size of the pinned hub panel in MB, 64), "fix_eps" (the float64 fix-up of
+ * lt_attack_efficient treats |H| ≤ 2^-fix_eps·max(f,64)/64·max|H[r,:]| as undecidable in float32 and re-evaluates it; 19),
+ * "spmm_stage" (cp.async shared-memory staging of the gathered rows, 0), "spmm_segmeta" (work-item table instead of a
+ * binary search in the restricted SpMM, 1).
  * ------------------------------------------------------------------------------------------- */
 int lt_set_option(const char* name_host, int value);
 int lt_get_option(const char* name_host, int* value_host);

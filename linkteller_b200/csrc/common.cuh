@@ -80,9 +80,9 @@ int device_alloc(void** out, size_t bytes, cudaStream_t s);
 
 // ---- process-wide options (lt_set_option / lt_get_option).  Initial values come from the environment ONCE, at the
 // first query (LT_NO_OVERLAP, LT_NO_SIGN_PATH, LT_TC_WS, LT_SPMM_PANEL, LT_SPMM_PANEL_MB, LT_SPMM_PANEL_LMIN,
-// LT_SPMM_HUB, LT_SPMM_HUB_MB); after that no call reads the environment.
+// LT_SPMM_HUB, LT_SPMM_HUB_MB, LT_FIX_EPS); after that no call reads the environment.
 enum Opt { OPT_OVERLAP = 0, OPT_SIGN_PATH, OPT_TC_WS, OPT_SPMM_PANEL, OPT_SPMM_PANEL_MB, OPT_SPMM_PANEL_LMIN, OPT_SPMM_HUB,
-           OPT_SPMM_HUB_MB, OPT_COUNT };
+           OPT_SPMM_HUB_MB, OPT_FIX_EPS, OPT_SPMM_STAGE, OPT_SPMM_SEGMETA, OPT_COUNT };
 int opt(Opt which);
 
 // ---- phase timers (lt_prof_*): CUDA events on the launching stream, only when enabled ----
@@ -146,6 +146,24 @@ __device__ __forceinline__ int64_t upper_bound(const T* __restrict__ a, int64_t 
 
 // non-zeros per warp work item of the CSR SpMM (spmm.cu); the attack plan sizes the segment list with it
 constexpr int SPMM_SEG = 256;
+
+// ---- hub panel of the restricted SpMM (spmm.cu): the most-gathered rows of the dense operand in one L2-resident copy ----
+struct HubView {
+    const uint32_t* bits;    // [ceil(n/32)] membership bitmap over the columns
+    const int32_t* pref;     // [ceil(n/32) + 1] exclusive scan of the words' popcounts: slot of a hub column
+    const float4* rows4;     // compact copy of the hub rows, row stride ld4 float4
+    uint32_t ld4;
+};
+struct HubPanel {
+    HubView view{nullptr, nullptr, nullptr, 0};
+    void* base = nullptr;    // start and size of the persisting access-policy window
+    size_t bytes = 0;
+    bool valid = false;
+};
+struct Scratch;
+bool hub_applicable(int32_t n_cols, int64_t ldb, int32_t d, const float* B);
+int hub_prepare(const int32_t* indptr, int32_t n, const float* B, int64_t ldb, int32_t d, HubPanel* out, Scratch& scratch,
+                cudaStream_t s);
 
 // ---- primitives implemented in scan.cu / radix_sort.cu ----
 // out has n+1 entries: out[0] = 0, out[k] = sum(in[0..k)), out[n] = total.  in may alias out.

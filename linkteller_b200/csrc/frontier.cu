@@ -33,7 +33,8 @@ int spmm_csr_f32(const int32_t* indptr, const int32_t* indices, const float* val
                  float* C, int64_t ldc, cudaStream_t s);
 int spmm_csr_f32_seg(const int32_t* indptr, const int32_t* indices, const float* values, int32_t n_cols,
                      const int32_t* rows, int32_t n_rows, const float* B, int64_t ldb, int32_t d, const float* bias, int relu,
-                     float* C, int64_t ldc, const int32_t* seg_off_known, int64_t total_seg_known, cudaStream_t s);
+                     float* C, int64_t ldc, const int32_t* seg_off_known, int64_t total_seg_known, cudaStream_t s,
+                     const HubPanel* hub = nullptr);
 
 }  // namespace lt
 
@@ -531,97 +532,272 @@ __global__ void k_row_absmax(const float* __restrict__ P, int64_t ldp, int32_t r
     if (lane == 0) pmax[j] = m;
 }
 
-// One thread per incidence: queue those whose row has an |H| small enough for a ReLU to switch under this
-// perturbation (|H| ≤ |δ·a|·max|P[v]|, with a margin for the rounding of the bound itself).  The order of the queue
-// does not matter: every entry patches its own ΔQ row.
+// ------------------------------------------------------------------------------------ exact fix-up (float64)
+// Where a ReLU of row r switches under the perturbation — |H[r,k]| ≤ |δ·Â[r,v]·P[v,k]| — the finite difference is
+// −H/δ or (H + δ·a·P)/δ: it depends on the VALUE of H[r,k] to within δ·a·|P|·tol.  With δ = 1e-4 that is 1e-9 … 1e-6
+// absolute while a float32 evaluation of H (a sum over deg(r)·f products) is only good to ~1e-7·Σ|terms|: on the
+// twitch-shaped config (|H| ~ 3, f = 3170) the float32 result of such a unit is off by tens of per cent, and the
+// influence entries it feeds by up to 7 % (measured against the reference run in float64).  Those units are rare
+// (a few per thousand incidences), so they are re-evaluated exactly: the incidences with a unit within reach of a
+// switch — or whose sign float32 cannot decide, |H| ≤ ε_H(r) = 2^-fix_eps·max|H[r,:]| — are queued, row r of Â·X is
+// gathered in float64 (k_fix_gather, segments of FIX_SEG entries summed in order: deterministic), H[r,:] and P[v,:]
+// are evaluated in float64 from it (layers.py:31-34 restated), ΔR is taken case by case in float64, and the
+// difference to what F1 used for the unit (sign-mask or value form, recomputed here bit for bit) goes through W2
+// into ΔQ[e,:].  The queue length is read back while F1 runs (pinned word + event), so no launch bubble is added.
+constexpr int FIX_SEG = 128;
+
+struct FixCtx {                       // what the exact fix-up needs beyond the plan: the graph, X and layer 1
+    const int32_t* indptr; const int32_t* indices; const float* values;
+    const float* X; int64_t ldx; int32_t f;
+    const float* W1; const float* b1;
+    const int32_t* v_nodes;           // node id of perturbed node j (test_nodes + lo)
+    const int32_t* rows;              // node id of compact frontier row ρ (null: s_row already holds node ids)
+};
+
+__device__ __forceinline__ int32_t fix_nseg(int32_t len) { return len <= FIX_SEG ? 1 : (len + FIX_SEG - 1) / FIX_SEG; }
+
+// sign-mask path: thread per incidence; queue it when the row's smallest |H| is within reach of a switch or of the
+// float32 uncertainty of H.  counters[0] = queue length, counters[1] = Σ gather segments of the queued rows.
 __global__ void k_slow_mark(const int32_t* __restrict__ s_j, const int32_t* __restrict__ s_rho, const float* __restrict__ s_a,
-                            int64_t E, const uint32_t* __restrict__ minabs_bits, const float* __restrict__ pmax, float delta,
-                            int32_t* __restrict__ slow_list, int32_t* __restrict__ n_slow) {
+                            int64_t E, const uint32_t* __restrict__ minabs_bits, int32_t R, const float* __restrict__ pmax,
+                            float delta, float eps_scale, const int32_t* __restrict__ rows, const int32_t* __restrict__ indptr,
+                            int32_t* __restrict__ slow_list, int32_t* __restrict__ counters) {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= E) return;
-    const float thr = fabsf(delta * s_a[e]) * pmax[s_j[e]] * 1.001f;
-    if (!(__uint_as_float(minabs_bits[s_rho[e]]) > thr)) slow_list[atomicAdd(n_slow, 1)] = (int32_t)e;
+    const int32_t rho = s_rho[e];
+    const float thr = fabsf(delta * s_a[e]) * pmax[s_j[e]] * 1.001f + eps_scale * __uint_as_float(minabs_bits[R + rho]);
+    if (!(__uint_as_float(minabs_bits[rho]) > thr)) {
+        slow_list[atomicAdd(&counters[0], 1)] = (int32_t)e;
+        const int32_t r = rows ? rows[rho] : rho;
+        atomicAdd(&counters[1], fix_nseg(indptr[r + 1] - indptr[r]));
+    }
 }
 
-// The queued incidences, one warp each,
-// grid-stride over the queue.  H[r,:] = AX[r,:]·W1 + b1 is recomputed in fp32 (a lane owns the hidden units lane,
-// lane+32, …: up to eight independent accumulators, W1 rows read coalesced), ΔR is evaluated case by case as in
-// DeltaRProd, and the difference to the masked value — non-zero only where a ReLU switches — is pushed through W2
-// into ΔQ[e,:].
+// value path (H rows stored): warp per incidence, same test evaluated unit by unit on the stored row
 __global__ void __launch_bounds__(256)
-k_flip_fix(const int32_t* __restrict__ slow_list, const int32_t* __restrict__ n_slow, const int32_t* __restrict__ s_j,
-           const int32_t* __restrict__ s_rho, const float* __restrict__ s_a, const float* __restrict__ AX, int64_t ldax,
-           int32_t f, const float* __restrict__ W1, const float* __restrict__ b1, const float* __restrict__ P, int64_t ldp,
-           const int32_t* __restrict__ p_index, const uint32_t* __restrict__ sign_words, int32_t wpr,
-           const float* __restrict__ W2, int32_t h, int32_t c, float delta, float inv_delta, float* __restrict__ dq,
-           int32_t lddq) {
+k_slow_mark_values(const int32_t* __restrict__ s_j, const int32_t* __restrict__ s_row, const float* __restrict__ s_a, int64_t E,
+                   const float* __restrict__ H, int64_t ldh, const float* __restrict__ P, int64_t ldp,
+                   const int32_t* __restrict__ p_index, int32_t h, float delta, float eps_scale,
+                   const int32_t* __restrict__ rows, const int32_t* __restrict__ indptr, int32_t* __restrict__ slow_list,
+                   int32_t* __restrict__ counters) {
     const int lane = threadIdx.x & 31;
-    const int32_t total = *n_slow;
-    const int32_t stride = (int32_t)((gridDim.x * blockDim.x) >> 5);
-    for (int32_t q = (int32_t)((blockIdx.x * blockDim.x + threadIdx.x) >> 5); q < total; q += stride) {
-        const int64_t e = slow_list[q];
-        const int32_t j = s_j[e], rho = s_rho[e];
-        const float a = s_a[e];
-        const float* ax = AX + (int64_t)rho * ldax;
-        const float* prow = P + (int64_t)(p_index ? p_index[j] : j) * ldp;
-        const float da = delta * a;
-        // hidden units of this lane inside a block of 256: 4·lane … +3 and 128 + 4·lane … +3 (h % 4 == 0), so a W1
-        // row costs two 16-byte loads per lane; eight rows are fetched before their 64 FMAs — loaded one scalar at a
-        // time and consumed at once, the 800 dependent loads of an entry took 150 µs (ncu r1j: FFMA on long_scoreboard)
-        for (int k0 = 0; k0 < h; k0 += 256) {
-            const int ka = k0 + 4 * lane, kb2 = k0 + 128 + 4 * lane;
-            const bool va = ka < h, vb = kb2 < h;
-            float4 ha = va ? make_float4(b1[ka], b1[ka + 1], b1[ka + 2], b1[ka + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
-            float4 hb = vb ? make_float4(b1[kb2], b1[kb2 + 1], b1[kb2 + 2], b1[kb2 + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
-            const int ca = va ? ka : 0, cb = vb ? kb2 : 0;                 // clamped columns: loads stay unconditional
-            for (int i0 = 0; i0 < f; i0 += 32) {
-                const float av = i0 + lane < f ? ax[i0 + lane] : 0.f;      // 32 entries of the AX row, one per lane
-                for (int u0 = 0; u0 < 32 && i0 + u0 < f; u0 += 8) {
-                    float4 wa[8], wb[8];
+    const int64_t e = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (e >= E) return;
+    const int32_t j = s_j[e];
+    const float* hr = H + (int64_t)s_row[e] * ldh;
+    const float* pr = P + (int64_t)(p_index ? p_index[j] : j) * ldp;
+    const float da = fabsf(delta * s_a[e]) * 1.001f;
+    float mx = 0.f;
+    for (int k = lane; k < h; k += 32) mx = fmaxf(mx, fabsf(hr[k]));
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const int i = min(i0 + u0 + u, f - 1);             // rows past f: re-read the last row, weight 0
-                        wa[u] = __ldg(reinterpret_cast<const float4*>(W1 + (int64_t)i * h + ca));
-                        wb[u] = __ldg(reinterpret_cast<const float4*>(W1 + (int64_t)i * h + cb));
-                    }
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(LT_FULL, mx, o));
+    const float eps = eps_scale * mx;
+    bool hit = false;
+    for (int k = lane; k < h; k += 32) hit |= !(fabsf(hr[k]) > da * fabsf(pr[k]) + eps);
+    if (__any_sync(LT_FULL, hit) && lane == 0) {
+        slow_list[atomicAdd(&counters[0], 1)] = (int32_t)e;
+        const int32_t r = rows ? rows[s_row[e]] : s_row[e];
+        atomicAdd(&counters[1], fix_nseg(indptr[r + 1] - indptr[r]));
+    }
+}
+
+__global__ void k_fix_nseg(const int32_t* __restrict__ slow_list, int32_t n_slow, const int32_t* __restrict__ s_row,
+                           const int32_t* __restrict__ rows, const int32_t* __restrict__ indptr, int32_t* __restrict__ nseg) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n_slow) return;
+    const int32_t rr = s_row[slow_list[q]];
+    const int32_t r = rows ? rows[rr] : rr;
+    nseg[q] = fix_nseg(indptr[r + 1] - indptr[r]);
+}
+
+// warp per gather segment g: part[g, i] = Σ_{t in segment} (double)Â[r,t]·(double)X[col_t, i], entries in CSR order.
+// The (column, value) pairs of a segment are read 32 at a time and broadcast by shuffle; eight rows of X are in flight
+// per lane before their FMAs — walked one dependent load at a time, a 512-entry segment took 0.5 ms (r2c).
+__global__ void __launch_bounds__(256)
+k_fix_gather(const int32_t* __restrict__ slow_list, int32_t n_slow, const int32_t* __restrict__ seg_off,
+             const int32_t* __restrict__ s_row, FixCtx c, double* __restrict__ part) {
+    const int lane = threadIdx.x & 31;
+    const int nfb = (c.f + 127) / 128;                     // a warp takes one block of 128 features of one segment
+    const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t g = wid / nfb;
+    if (g >= seg_off[n_slow]) return;
+    const int32_t q = (int32_t)upper_bound(seg_off, 0, (int64_t)n_slow + 1, (int32_t)g) - 1;
+    const int32_t rr = s_row[slow_list[q]];
+    const int32_t r = c.rows ? c.rows[rr] : rr;
+    const int32_t t0 = c.indptr[r] + ((int32_t)g - seg_off[q]) * FIX_SEG;
+    const int32_t t1 = min(c.indptr[r + 1], t0 + FIX_SEG);
+    double* dst = part + (int64_t)g * c.f;
+    {
+        const int i0 = (int)(wid % nfb) * 128;             // 4 features per lane: i0 + lane + 32u
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+        int ic[4];
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const float ai = __shfl_sync(LT_FULL, av, u0 + u);  // 0 for rows past f
-                        fma4(ha, ai, wa[u]);
-                        fma4(hb, ai, wb[u]);
-                    }
+        for (int u = 0; u < 4; ++u) ic[u] = min(i0 + lane + 32 * u, c.f - 1);    // clamped: loads stay unconditional
+        for (int32_t base = t0; base < t1; base += 32) {
+            const int32_t t = base + lane;
+            const int64_t mo = t < t1 ? (int64_t)c.indices[t] * c.ldx : 0;
+            const float mv = t < t1 ? c.values[t] : 0.f;
+            const int cnt = min(32, t1 - base);
+            for (int k = 0; k < cnt; k += 8) {
+                float x[8][4];
+#pragma unroll
+                for (int e8 = 0; e8 < 8; ++e8) {
+                    const float* xr = c.X + __shfl_sync(LT_FULL, mo, (k + e8) & 31);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) x[e8][u] = __ldg(xr + ic[u]);
                 }
-            }
-            const float hs[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
 #pragma unroll
-            for (int t = 0; t < 8; ++t) {
-                const int k = (t < 4 ? ka : kb2) + (t & 3);
-                float d = 0.f;
-                if (k < h) {
-                    const float p = prow[k];
-                    const float hp = fmaf(da, p, hs[t]);
-                    // one rounded product for both terms: written as a·p twice, the compiler may contract the
-                    // subtraction into an fma and d becomes the product's rounding error instead of 0
-                    const float ap = __fmul_rn(a, p);
-                    float exact;
-                    if (hs[t] > 0.f) exact = hp > 0.f ? ap : -hs[t] * inv_delta;
-                    else exact = hp > 0.f ? hp * inv_delta : 0.f;
-                    const uint32_t bit = (sign_words[(int64_t)rho * wpr + (k >> 5)] >> (k & 31)) & 1u;
-                    d = exact - (bit ? ap : 0.f);
-                }
-                uint32_t m = __ballot_sync(LT_FULL, d != 0.f);
-                while (m) {
-                    const int src = __ffs(m) - 1;
-                    m &= m - 1;
-                    const float dk = __shfl_sync(LT_FULL, d, src);
-                    const int ks = (t < 4 ? k0 + 4 * src : k0 + 128 + 4 * src) + (t & 3);
-                    const float* w2 = W2 + (int64_t)ks * c;
-                    for (int col = lane; col < c; col += 32) dq[e * lddq + col] = fmaf(dk, w2[col], dq[e * lddq + col]);
+                for (int e8 = 0; e8 < 8; ++e8) {
+                    const double a = (double)__shfl_sync(LT_FULL, mv, (k + e8) & 31);      // 0 past the end of the segment
+                    if (k + e8 < cnt) {
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) acc[u] = fma(a, (double)x[e8][u], acc[u]);
+                    }
                 }
             }
         }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (i0 + lane + 32 * u < c.f) dst[i0 + lane + 32 * u] = acc[u];
     }
 }
+
+// MODE 0: sign-mask form (what MaskProd fed F1), MODE 1: value form (DeltaRProd on the stored H row).
+// One CTA per queued incidence (grid-stride); shared: d[h] corrections.
+template <int MODE>
+__global__ void __launch_bounds__(256)
+k_exact_fix(const int32_t* __restrict__ slow_list, int32_t n_slow, const int32_t* __restrict__ seg_off,
+            const int32_t* __restrict__ s_j, const int32_t* __restrict__ s_row, const float* __restrict__ s_a, FixCtx c,
+            double* __restrict__ part, const float* __restrict__ P, int64_t ldp, const int32_t* __restrict__ p_index,
+            const uint32_t* __restrict__ sign_words, int32_t wpr, const uint32_t* __restrict__ maxabs_bits,
+            const float* __restrict__ H, int64_t ldh, const float* __restrict__ W2, int32_t h, int32_t cdim, float delta,
+            float inv_delta, float eps_scale, float* __restrict__ dq, int32_t lddq) {
+    extern __shared__ float dsm[];                      // [h]
+    for (int32_t q = blockIdx.x; q < n_slow; q += gridDim.x) {
+        const int64_t e = slow_list[q];
+        const int32_t j = s_j[e], rr = s_row[e];
+        const float a = s_a[e];
+        const int32_t g0 = seg_off[q], g1 = seg_off[q + 1];
+        double* ax = part + (int64_t)g0 * c.f;          // the row of Â·X in float64: segments summed in order, in place
+        for (int i = threadIdx.x; i < c.f; i += blockDim.x) {
+            double sum = ax[i];
+            int32_t g = g0 + 1;
+            for (; g + 4 <= g1; g += 4) {                 // four loads in flight, added in segment order
+                const double p0 = part[(int64_t)g * c.f + i], p1 = part[(int64_t)(g + 1) * c.f + i],
+                             p2 = part[(int64_t)(g + 2) * c.f + i], p3 = part[(int64_t)(g + 3) * c.f + i];
+                sum += p0; sum += p1; sum += p2; sum += p3;
+            }
+            for (; g < g1; ++g) sum += part[(int64_t)g * c.f + i];
+            ax[i] = sum;
+        }
+        __syncthreads();
+        const float* xv = c.X + (int64_t)c.v_nodes[j] * c.ldx;
+        const float* prow = P + (int64_t)(p_index ? p_index[j] : j) * ldp;
+        for (int k = threadIdx.x; k < h; k += blockDim.x) {
+            double hd = (double)c.b1[k], pd = 0.0;
+            for (int i = 0; i < c.f; ++i) {
+                const double w = (double)c.W1[(int64_t)i * h + k];
+                hd = fma(ax[i], w, hd);                  // H[r,k] = (Â·X)[r,:]·W1[:,k] + b1[k]
+                pd = fma((double)xv[i], w, pd);          // P[v,k] = x_v·W1[:,k]
+            }
+            const double dap = (double)delta * (double)a * pd;
+            float d = 0.f;
+            float eps;
+            float cur;
+            const float p32 = prow[k];
+            const float ap = __fmul_rn(a, p32);
+            if (MODE == 0) {
+                eps = eps_scale * __uint_as_float(maxabs_bits[rr]);
+                const uint32_t bit = (sign_words[(int64_t)rr * wpr + (k >> 5)] >> (k & 31)) & 1u;
+                cur = bit ? ap : 0.f;
+            } else {
+                const float* hrow = H + (int64_t)rr * ldh;
+                float mx = 0.f;                          // every thread needs the row's scale: cheap (h ≤ a few hundred)
+                for (int kk = 0; kk < h; ++kk) mx = fmaxf(mx, fabsf(hrow[kk]));
+                eps = eps_scale * mx;
+                const float hh = hrow[k];
+                const float hp = fmaf(__fmul_rn(delta, a), p32, hh);
+                if (hh > 0.f) cur = hp > 0.f ? ap : __fmul_rn(-hh, inv_delta);
+                else cur = hp > 0.f ? __fmul_rn(hp, inv_delta) : 0.f;
+            }
+            if (fabs(hd) <= fabs(dap) * 1.01 + 2.0 * (double)eps) {
+                const double hp = hd + dap;
+                double exact;
+                if (hd > 0.0) exact = hp > 0.0 ? (double)a * pd : -hd / (double)delta;
+                else exact = hp > 0.0 ? hp / (double)delta : 0.0;
+                d = (float)exact - cur;
+            }
+            dsm[k] = d;
+        }
+        __syncthreads();
+        for (int col = threadIdx.x; col < cdim; col += blockDim.x) {
+            float acc = 0.f;
+            bool any = false;
+            for (int k = 0; k < h; ++k) {
+                const float dk = dsm[k];
+                if (dk != 0.f) { acc = fmaf(dk, W2[(int64_t)k * cdim + col], acc); any = true; }
+            }
+            if (any) dq[e * lddq + col] += acc;
+        }
+        __syncthreads();
+    }
+}
+
+// host side of the fix-up.  `counters` (device: queue length, Σ segments) were filled by a marking kernel already queued
+// on `s`; `queue_f1` launches F1 — it is called after the read-back of the counters has been queued, so the host
+// learns the queue length while F1 runs.
+struct FixPinned {
+    int32_t* h = nullptr;
+    ~FixPinned() { if (h) cudaFreeHost(h); }
+};
+
+template <typename LaunchF1>
+static int exact_fix_run(int mode, const lt_plan* p, const int32_t* s_row, const FixCtx& ctx, int32_t* slow_list,
+                         int32_t* counters, const float* P, int64_t ldp, const int32_t* p_index,
+                         const uint32_t* sign_words, int32_t wpr, const uint32_t* maxabs_bits, const float* H, int64_t ldh,
+                         const float* W2, int32_t h, int32_t c, float delta, float eps_scale, float* dq, int32_t lddq,
+                         int32_t* n_fixed_host, cudaStream_t s, LaunchF1 queue_f1) {
+    static thread_local FixPinned pin;
+    if (!pin.h) LT_CUDA(cudaHostAlloc((void**)&pin.h, 16, cudaHostAllocDefault));
+    cudaEvent_t ev;
+    LT_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    struct EvGuard { cudaEvent_t e; ~EvGuard() { cudaEventDestroy(e); } } evg{ev};
+    LT_CUDA(cudaMemcpyAsync(pin.h, counters, 8, cudaMemcpyDeviceToHost, s));
+    LT_CUDA(cudaEventRecord(ev, s));
+    LT_TRY(queue_f1());
+    LT_CUDA(cudaEventSynchronize(ev));
+    const int32_t n_slow = pin.h[0], total_seg = pin.h[1];
+    if (n_fixed_host) *n_fixed_host = n_slow;
+    if (n_slow == 0) return LT_OK;
+    ProfScope prof("frontier_fix", s);
+    Scratch scratch(s);
+    int32_t* seg_off;
+    double* part;
+    LT_TRY(scratch.alloc(&seg_off, (size_t)n_slow + 1));
+    LT_TRY(scratch.alloc(&part, (size_t)total_seg * ctx.f));
+    k_fix_nseg<<<(unsigned)ceil_div(n_slow, 256), 256, 0, s>>>(slow_list, n_slow, s_row, ctx.rows, ctx.indptr, seg_off);
+    LT_LAUNCH_CHECK();
+    LT_TRY(exclusive_scan_i32(seg_off, seg_off, n_slow, s));
+    k_fix_gather<<<(unsigned)ceil_div((int64_t)total_seg * ((ctx.f + 127) / 128) * 32, 256), 256, 0, s>>>(slow_list, n_slow, seg_off,
+                                                                                                          s_row, ctx, part);
+    LT_LAUNCH_CHECK();
+    const unsigned grid = (unsigned)(n_slow < num_sms() * 4 ? n_slow : num_sms() * 4);
+    const size_t smem = (size_t)h * sizeof(float);
+    if (mode == 0)
+        k_exact_fix<0><<<grid, 256, smem, s>>>(slow_list, n_slow, seg_off, p->s_j, s_row, p->s_a, ctx, part, P, ldp, p_index,
+                                               sign_words, wpr, maxabs_bits, H, ldh, W2, h, c, delta, 1.0f / delta, eps_scale, dq, lddq);
+    else
+        k_exact_fix<1><<<grid, 256, smem, s>>>(slow_list, n_slow, seg_off, p->s_j, s_row, p->s_a, ctx, part, P, ldp, p_index,
+                                               sign_words, wpr, maxabs_bits, H, ldh, W2, h, c, delta, 1.0f / delta, eps_scale, dq, lddq);
+    LT_LAUNCH_CHECK();
+    return LT_OK;
+}
+
+// ε_H(r) = eps_scale·max|H[r,:]|: what float32 cannot decide.  Measured on the B200 (profiles/h_error_probe.py, 3xTF32
+// products with float32 accumulation, against float64): max over rows of |H32 − H64| / max|H[r,:]| = 1.1e-6 at f = 50,
+// 1.7e-6 at f = 100, 6.8e-6 at f = 500, 4.1e-5 at f = 3170 — it grows linearly with the depth f of the first-layer
+// product.  eps_scale = 2^-fix_eps·max(f,64)/64 (fix_eps = 19) stays 1.7-2.3x above those.
+static inline float fix_eps_scale(int32_t f) { return ldexpf(1.0f, -opt(OPT_FIX_EPS)) * (float)(f > 64 ? f : 64) / 64.f; }
 
 static int plan_own(lt_plan* p, void* ptr) {
     if (p->n_owned >= 24) { set_error("plan: too many buffers"); return LT_ERR_INTERNAL; }
@@ -839,9 +1015,37 @@ static inline bool frontier_use_tc(int64_t E, int32_t h, int32_t c) {
 }
 static inline int32_t frontier_lddq(int64_t E, int32_t h, int32_t c) { return frontier_use_tc(E, h, c) ? (c + 3) / 4 * 4 : c; }
 
+static int frontier_dq_launch(const lt_plan* p, const int32_t* h_index, const float* H, int64_t ldh, const float* P, int64_t ldp,
+                              const int32_t* p_index, const float* W2, int32_t h, int32_t c, float delta, float* dq,
+                              cudaStream_t s);
+
+// `fix` (nullable): the graph / X / layer-1 weights the float64 fix-up needs.  Without it (lt_influence_rows: the caller
+// hands in H_R only) the units where a ReLU switches keep their float32 evaluation.
 static int frontier_dq(const lt_plan* p, const int32_t* h_index, const float* H, int64_t ldh, const float* P, int64_t ldp,
                        const int32_t* p_index, const float* W2, int32_t h, int32_t c, float delta, float* dq,
-                       cudaStream_t s) {
+                       cudaStream_t s, const FixCtx* fix = nullptr, int32_t* n_fixed_host = nullptr) {
+    if (n_fixed_host) *n_fixed_host = 0;
+    if (!fix || p->E == 0) return frontier_dq_launch(p, h_index, H, ldh, P, ldp, p_index, W2, h, c, delta, dq, s);
+    Scratch scratch(s);
+    int32_t *slow_list, *counters;
+    LT_TRY(scratch.alloc(&slow_list, (size_t)p->E));
+    LT_TRY(scratch.alloc(&counters, 2));
+    LT_CUDA(cudaMemsetAsync(counters, 0, 8, s));
+    const float eps_scale = fix_eps_scale(fix->f);
+    {
+        ProfScope prof("frontier_dq", s);
+        k_slow_mark_values<<<(unsigned)ceil_div(p->E * 32, 256), 256, 0, s>>>(p->s_j, h_index, p->s_a, p->E, H, ldh, P, ldp, p_index, h,
+                                                                              delta, eps_scale, fix->rows, fix->indptr, slow_list, counters);
+        LT_LAUNCH_CHECK();
+    }
+    return exact_fix_run(1, p, h_index, *fix, slow_list, counters, P, ldp, p_index, nullptr, 0, nullptr, H, ldh, W2, h, c, delta,
+                         eps_scale, dq, frontier_lddq(p->E, h, c), n_fixed_host, s,
+                         [&]() { return frontier_dq_launch(p, h_index, H, ldh, P, ldp, p_index, W2, h, c, delta, dq, s); });
+}
+
+static int frontier_dq_launch(const lt_plan* p, const int32_t* h_index, const float* H, int64_t ldh, const float* P, int64_t ldp,
+                              const int32_t* p_index, const float* W2, int32_t h, int32_t c, float delta, float* dq,
+                              cudaStream_t s) {
     const int64_t E = p->E;
     if (E == 0) return LT_OK;
     if (h % 4 != 0 || ldh % 4 != 0 || ldp % 4 != 0 || (uintptr_t)H % 16 || (uintptr_t)P % 16) {
@@ -901,50 +1105,57 @@ static int frontier_dq(const lt_plan* p, const int32_t* h_index, const float* H,
     return LT_OK;
 }
 
-// F1 from the sign mask of H_R (see MaskProd): ΔQ = (mask ⊙ a·P[v])·W2 on the tensor cores, then k_flip_fix
+// F1 from the sign mask of H_R (see MaskProd): ΔQ = (mask ⊙ a·P[v])·W2 on the tensor cores, then the float64 fix-up
 static int frontier_dq_signs(const lt_plan* p, const uint32_t* sign_words, int32_t wpr, const uint32_t* minabs_bits,
-                             const float* AX, int64_t ldax, int32_t f, const float* W1, const float* b1, const float* P,
-                             int64_t ldp, const int32_t* p_index, const float* W2, int32_t h, int32_t c, float delta,
-                             float* dq, int32_t* n_fixed, cudaStream_t s) {
+                             const FixCtx& fix, const float* P, int64_t ldp, const int32_t* p_index, const float* W2,
+                             int32_t h, int32_t c, float delta, float* dq, int32_t* n_fixed_host, cudaStream_t s) {
     const int64_t E = p->E;
+    if (n_fixed_host) *n_fixed_host = 0;
     if (E == 0) return LT_OK;
     Scratch scratch(s);
     const int32_t lddq = frontier_lddq(E, h, c);
     float* pmax;
-    int32_t* slow_list;
+    int32_t *slow_list, *counters;
     LT_TRY(scratch.alloc(&pmax, (size_t)p->Ts));
     LT_TRY(scratch.alloc(&slow_list, (size_t)E));
-    ProfScope prof("frontier_dq", s);
-    k_row_absmax<<<(unsigned)ceil_div((int64_t)p->Ts * 32, 256), 256, 0, s>>>(P, ldp, p->Ts, h, pmax);
-    LT_LAUNCH_CHECK();
+    LT_TRY(scratch.alloc(&counters, 2));
     const int nt = tc_pick_nt(c);
     const int32_t n_pad = nt, kchunks = tc_kchunks(h);
     uint32_t* img;
     LT_TRY(scratch.alloc(&img, (size_t)kchunks * 2 * n_pad * TC_BK));
-    LT_TRY(tc_prepack_b(W2, c, 0, c, h, n_pad, img, s));
-    k_slow_mark<<<(unsigned)ceil_div(E, 256), 256, 0, s>>>(p->s_j, p->s_rho, p->s_a, E, minabs_bits, pmax, delta, slow_list, n_fixed);
-    LT_LAUNCH_CHECK();
-    const MaskProd prod{p->s_j, p->s_rho, p->s_a, p_index, sign_words, wpr, P, ldp};
-    if (tc_use_ws()) {
-        switch (nt) {
-            case 32: LT_TRY((launch_ws<32>(prod, img, nullptr, 0, dq, lddq, (int32_t)E, c, h, n_pad, kchunks, s))); break;
-            case 48: LT_TRY((launch_ws<48>(prod, img, nullptr, 0, dq, lddq, (int32_t)E, c, h, n_pad, kchunks, s))); break;
-            case 64: LT_TRY((launch_ws<64>(prod, img, nullptr, 0, dq, lddq, (int32_t)E, c, h, n_pad, kchunks, s))); break;
-            case 128: LT_TRY((launch_ws<128>(prod, img, nullptr, 0, dq, lddq, (int32_t)E, c, h, n_pad, kchunks, s))); break;
-            default: LT_TRY((launch_ws<256>(prod, img, nullptr, 0, dq, lddq, (int32_t)E, c, h, n_pad, kchunks, s))); break;
-        }
-    } else
-    switch (nt) {
-        case 32: LT_TRY((launch_tc<32, 2>(prod, img, nullptr, 0, dq, lddq, (int32_t)E, c, h, n_pad, kchunks, s))); break;
-        case 48: LT_TRY((launch_tc<48, 2>(prod, img, nullptr, 0, dq, lddq, (int32_t)E, c, h, n_pad, kchunks, s))); break;
-        case 64: LT_TRY((launch_tc<64, 2>(prod, img, nullptr, 0, dq, lddq, (int32_t)E, c, h, n_pad, kchunks, s))); break;
-        case 128: LT_TRY((launch_tc<128, 1>(prod, img, nullptr, 0, dq, lddq, (int32_t)E, c, h, n_pad, kchunks, s))); break;
-        default: LT_TRY((launch_tc<256, 1>(prod, img, nullptr, 0, dq, lddq, (int32_t)E, c, h, n_pad, kchunks, s))); break;
+    const float eps_scale = fix_eps_scale(fix.f);
+    {
+        ProfScope prof("frontier_dq", s);
+        LT_CUDA(cudaMemsetAsync(counters, 0, 8, s));
+        k_row_absmax<<<(unsigned)ceil_div((int64_t)p->Ts * 32, 256), 256, 0, s>>>(P, ldp, p->Ts, h, pmax);
+        LT_LAUNCH_CHECK();
+        LT_TRY(tc_prepack_b(W2, c, 0, c, h, n_pad, img, s));
+        k_slow_mark<<<(unsigned)ceil_div(E, 256), 256, 0, s>>>(p->s_j, p->s_rho, p->s_a, E, minabs_bits, p->R, pmax, delta, eps_scale,
+                                                               fix.rows, fix.indptr, slow_list, counters);
+        LT_LAUNCH_CHECK();
     }
-    k_flip_fix<<<(unsigned)num_sms() * 2, 256, 0, s>>>(slow_list, n_fixed, p->s_j, p->s_rho, p->s_a, AX, ldax, f, W1, b1, P, ldp,
-                                                       p_index, sign_words, wpr, W2, h, c, delta, 1.0f / delta, dq, lddq);
-    LT_LAUNCH_CHECK();
-    return LT_OK;
+    const MaskProd prod{p->s_j, p->s_rho, p->s_a, p_index, sign_words, wpr, P, ldp};
+    auto queue_f1 = [&]() -> int {
+        ProfScope prof("frontier_dq", s);
+        if (tc_use_ws()) {
+            switch (nt) {
+                case 32: return launch_ws<32>(prod, img, nullptr, 0, dq, lddq, (int32_t)E, c, h, n_pad, kchunks, s);
+                case 48: return launch_ws<48>(prod, img, nullptr, 0, dq, lddq, (int32_t)E, c, h, n_pad, kchunks, s);
+                case 64: return launch_ws<64>(prod, img, nullptr, 0, dq, lddq, (int32_t)E, c, h, n_pad, kchunks, s);
+                case 128: return launch_ws<128>(prod, img, nullptr, 0, dq, lddq, (int32_t)E, c, h, n_pad, kchunks, s);
+                default: return launch_ws<256>(prod, img, nullptr, 0, dq, lddq, (int32_t)E, c, h, n_pad, kchunks, s);
+            }
+        }
+        switch (nt) {
+            case 32: return launch_tc<32, 2>(prod, img, nullptr, 0, dq, lddq, (int32_t)E, c, h, n_pad, kchunks, s);
+            case 48: return launch_tc<48, 2>(prod, img, nullptr, 0, dq, lddq, (int32_t)E, c, h, n_pad, kchunks, s);
+            case 64: return launch_tc<64, 2>(prod, img, nullptr, 0, dq, lddq, (int32_t)E, c, h, n_pad, kchunks, s);
+            case 128: return launch_tc<128, 1>(prod, img, nullptr, 0, dq, lddq, (int32_t)E, c, h, n_pad, kchunks, s);
+            default: return launch_tc<256, 1>(prod, img, nullptr, 0, dq, lddq, (int32_t)E, c, h, n_pad, kchunks, s);
+        }
+    };
+    return exact_fix_run(0, p, p->s_rho, fix, slow_list, counters, P, ldp, p_index, sign_words, wpr, minabs_bits + p->R, nullptr, 0, W2,
+                         h, c, delta, eps_scale, dq, lddq, n_fixed_host, s, queue_f1);
 }
 
 // out[j,i] = ‖Σ_k w_k·ΔQ[e_k,:]‖₂ for every group of sorted records (F2)
@@ -992,7 +1203,7 @@ static int frontier_reduce(const uint64_t* rec_key, const uint64_t* rec_val, con
 
 int influence_rows(const lt_plan* p, const float* H_R, int64_t ldh, const float* P, int64_t ldp,
                    const int32_t* p_index, const float* W2, int32_t h, int32_t c, float delta, float* out,
-                   int64_t ldo, cudaStream_t s) {
+                   int64_t ldo, cudaStream_t s, const FixCtx* fix = nullptr, int32_t* n_fixed_host = nullptr) {
     const int64_t E = p->E, M = p->M;
     LT_CUDA(cudaMemset2DAsync(out, (size_t)ldo * 4, 0, (size_t)p->T * 4, (size_t)p->Ts, s));
     if (E == 0 || M == 0) return LT_OK;
@@ -1000,7 +1211,7 @@ int influence_rows(const lt_plan* p, const float* H_R, int64_t ldh, const float*
     float* dq;
     const int32_t lddq = frontier_lddq(E, h, c);
     LT_TRY(scratch.alloc(&dq, (size_t)E * lddq));
-    LT_TRY(frontier_dq(p, p->s_rho, H_R, ldh, P, ldp, p_index, W2, h, c, delta, dq, s));
+    LT_TRY(frontier_dq(p, p->s_rho, H_R, ldh, P, ldp, p_index, W2, h, c, delta, dq, s, fix, n_fixed_host));
     return frontier_reduce(p->rec_key, p->rec_val, p->grp_off, p->n_groups, p->big, p->n_big, M, dq, lddq, c, out, ldo, s);
 }
 
@@ -1137,8 +1348,12 @@ static int gcn3_chunk(const int32_t* indptr, const int32_t* indices, const float
                       const int32_t* test_nodes, int32_t T, int32_t lo, int32_t hi, const float* P, const float* H1,
                       int64_t ld1, const float* H2, int64_t ld2, const float* W2, const float* W3, int32_t h1, int32_t h2,
                       int32_t c, const int32_t* b_indptr, const int32_t* b_i, const float* b_w, float delta, float* out,
-                      int64_t ldo, Gcn3Info* info, cudaStream_t s) {
+                      int64_t ldo, Gcn3Info* info, const float* X, int64_t ldx, int32_t f, const float* W1, const float* b1,
+                      cudaStream_t s) {
     const int32_t Ts = hi - lo;
+    // layer 1 of GCN3 is the two-layer model's layer 1: same float64 fix-up of the switching units (s_node = node ids)
+    const FixCtx fix_ctx{indptr, indices, values, X, ldx, f, W1, b1, test_nodes + lo, nullptr};
+    const FixCtx* fix1 = &fix_ctx;
     LT_CUDA(cudaMemset2DAsync(out, (size_t)ldo * 4, 0, (size_t)T * 4, (size_t)Ts, s));
     lt_plan* plan = nullptr;
     LT_TRY(lt_plan_create(indptr, indices, values, n, test_nodes, T, lo, hi, (lt_stream_t)s, &plan));
@@ -1160,7 +1375,7 @@ static int gcn3_chunk(const int32_t* indptr, const int32_t* indices, const float
     k3_inc_rows<<<(unsigned)ceil_div(E1, 256), 256, 0, s>>>(plan->s_rho, plan->rows, E1, indptr, s_node, len1);
     LT_LAUNCH_CHECK();
     LT_TRY(exclusive_scan_i32_to_i64(len1, off2, E1, s));
-    LT_TRY(frontier_dq(plan, s_node, H1, ld1, P, ld1, test_nodes + lo, W2, h1, h2, delta, dq1, s));
+    LT_TRY(frontier_dq(plan, s_node, H1, ld1, P, ld1, test_nodes + lo, W2, h1, h2, delta, dq1, s, fix1));
     int64_t M2 = 0;
     LT_CUDA(cudaMemcpyAsync(&M2, off2 + E1, 8, cudaMemcpyDeviceToHost, s));
     LT_CUDA(cudaStreamSynchronize(s));
@@ -1327,7 +1542,7 @@ int attack_efficient3(const int32_t* indptr, const int32_t* indices, const float
         int64_t acc = 0;
         while (b < Ts && (b == a || acc + cost_h[b] <= cap)) acc += cost_h[b++];
         LT_TRY(gcn3_chunk(indptr, indices, values, n, test_nodes, T, lo + a, lo + b, P, H1, ld1, H2, ld2, W2, W3, h1, h2, c,
-                          b_indptr, b_i, b_w, delta, out + (int64_t)a * ldo, ldo, &info, s));
+                          b_indptr, b_i, b_w, delta, out + (int64_t)a * ldo, ldo, &info, X, ldx, f, W1, b1, s));
         a = b;
     }
     if (info_host) {
@@ -1406,8 +1621,9 @@ struct AttackCtx {
     bool sign_path = false;
     float *Pt = nullptr, *HR = nullptr, *AX = nullptr;
     uint32_t *signs = nullptr, *minabs = nullptr;
-    int32_t* n_fixed = nullptr;
     int32_t wpr = 0;
+    HubPanel hub;                       // hot rows of X kept in the L2 for the restricted SpMM (built on the side stream)
+    cudaEvent_t hub_ready = nullptr;
 };
 
 int attack_early(lt_plan* plan, void* vctx, cudaStream_t side) {
@@ -1419,8 +1635,9 @@ int attack_early(lt_plan* plan, void* vctx, cudaStream_t side) {
     {   // P_v = X[v]·W1 for the slice (gathered rows).  On the caller's stream: put on the side stream, its 64 big
         // tensor-core CTAs wait for whole SMs to drain of SpMM CTAs and hold the rest of the plan up behind them
         // (measured: SpMM 2.56 → 2.86 ms, side-stream plan 0.59 → 0.83 ms)
+        // float64 accumulation (algo 3): ΔR = Â[r,v]·P[v] carries these values straight into the result
         ProfScope prof("gemm_pv", s);
-        LT_TRY(gemm_f32(a.X, a.ldx, a.test_nodes + a.lo, a.W1, h, 0, nullptr, 0, a.Pt, h, Ts, h, f, 0, s));
+        LT_TRY(gemm_f32(a.X, a.ldx, a.test_nodes + a.lo, a.W1, h, 0, nullptr, 0, a.Pt, h, Ts, h, f, 3, s));
     }
     const bool aggregate_first = (f < h) && (f % 4 == 0) && (a.ldx % 4 == 0) && ((uintptr_t)a.X % 16 == 0);
     // sign-mask path: H_R is never written — the GEMM keeps one bit per element and the row's smallest magnitude
@@ -1430,19 +1647,19 @@ int attack_early(lt_plan* plan, void* vctx, cudaStream_t side) {
     if (aggregate_first) {
         // H_R = (Â[R,:]·X)·W1 + b1 : gathers f floats per non-zero instead of h
         LT_TRY(scratch.alloc(&a.AX, (size_t)R * f));
+        if (a.hub_ready) LT_CUDA(cudaStreamWaitEvent(s, a.hub_ready, 0));
         {
             ProfScope prof("spmm_ax", s);
             LT_TRY(spmm_csr_f32_seg(a.indptr, a.indices, a.values, n, plan->rows, R, a.X, a.ldx, f, nullptr, 0, a.AX, f,
-                                    plan->seg_off, plan->total_seg, s));
+                                    plan->seg_off, plan->total_seg, s, a.hub.valid ? &a.hub : nullptr));
         }
         ProfScope prof("gemm_h", s);
         if (a.sign_path) {
             a.wpr = (h + 31) / 32;
             LT_TRY(scratch.alloc(&a.signs, (size_t)R * a.wpr));
-            LT_TRY(scratch.alloc(&a.minabs, (size_t)R));
-            LT_TRY(scratch.alloc(&a.n_fixed, 1));
+            LT_TRY(scratch.alloc(&a.minabs, (size_t)R * 2));                  // [0,R) min |H[r,:]|, [R,2R) max |H[r,:]|
             LT_CUDA(cudaMemsetAsync(a.minabs, 0x7f, (size_t)R * 4, s));
-            LT_CUDA(cudaMemsetAsync(a.n_fixed, 0, 4, s));
+            LT_CUDA(cudaMemsetAsync(a.minabs + R, 0, (size_t)R * 4, s));
             LT_TRY(gemm_3xtf32_signs(a.AX, f, a.W1, h, a.b1, R, h, f, a.signs, a.minabs, s));
         } else {
             LT_TRY(scratch.alloc(&a.HR, (size_t)R * h));
@@ -1485,9 +1702,25 @@ extern "C" int lt_attack_efficient(const int32_t* indptr, const int32_t* indices
         Scratch scratch(s);
         AttackCtx a{indptr, indices, values, n, X, ldx, f, W1, b1, h, c, test_nodes, lo, s, &scratch};
         st = scratch.alloc(&a.Pt, (size_t)plan->Ts * h);
+        struct EvGuard { cudaEvent_t* e; ~EvGuard() { if (*e) cudaEventDestroy(*e); } } hub_guard{&a.hub_ready};
+        // hub panel of X for the aggregate-first SpMM: built next to the plan head, on the side stream
+        if (st == LT_OK && f < h && hub_applicable(n, ldx, f, X) && T >= 1024) {
+            cudaStream_t sd = overlap_enabled() ? side_stream() : nullptr;
+            cudaStream_t run = sd ? sd : s;
+            st = hub_prepare(indptr, n, X, ldx, f, &a.hub, scratch, run);
+            if (st == LT_OK && a.hub.valid && run != s) {
+                if (cudaEventCreateWithFlags(&a.hub_ready, cudaEventDisableTiming) != cudaSuccess ||
+                    cudaEventRecord(a.hub_ready, run) != cudaSuccess) {
+                    set_error("lt_attack_efficient: hub panel event failed");
+                    st = LT_ERR_CUDA;
+                }
+            }
+        }
         if (st == LT_OK)
             st = plan_build(plan, indptr, indices, values, test_nodes, s, overlap_enabled() ? attack_early : nullptr, &a);
         if (st == LT_OK && !overlap_enabled()) st = attack_early(plan, &a, s);
+        const FixCtx fix{indptr, indices, values, X, ldx, f, W1, b1, test_nodes + lo, plan->rows};
+        int32_t n_fixed = 0;
         if (st == LT_OK) {
             if (a.sign_path) {
                 const int32_t lddq = frontier_lddq(plan->E, h, c);
@@ -1499,22 +1732,18 @@ extern "C" int lt_attack_efficient(const int32_t* indptr, const int32_t* indices
                 if (st == LT_OK && plan->E > 0 && plan->M > 0) {
                     st = scratch.alloc(&dq, (size_t)plan->E * lddq);
                     if (st == LT_OK)
-                        st = frontier_dq_signs(plan, a.signs, a.wpr, a.minabs, a.AX, f, f, W1, b1, a.Pt, h, nullptr, W2, h, c, delta,
-                                               dq, a.n_fixed, s);
+                        st = frontier_dq_signs(plan, a.signs, a.wpr, a.minabs, fix, a.Pt, h, nullptr, W2, h, c, delta, dq, &n_fixed, s);
                     if (st == LT_OK)
                         st = frontier_reduce(plan->rec_key, plan->rec_val, plan->grp_off, plan->n_groups, plan->big, plan->n_big,
                                              plan->M, dq, lddq, c, out, ldo, s);
                 }
             } else {
-                st = influence_rows(plan, a.HR, h, a.Pt, h, nullptr, W2, h, c, delta, out, ldo, s);
+                st = influence_rows(plan, a.HR, h, a.Pt, h, nullptr, W2, h, c, delta, out, ldo, s, &fix, &n_fixed);
             }
         }
         if (st == LT_OK && info_host) {
             st = lt_plan_info(plan, h, c, info_host, stream);
-            int32_t nf = 0;
-            if (st == LT_OK && a.sign_path && cudaMemcpyAsync(&nf, a.n_fixed, 4, cudaMemcpyDeviceToHost, s) == cudaSuccess &&
-                cudaStreamSynchronize(s) == cudaSuccess)
-                info_host[7] = nf;      // incidences that took the exact (recomputed) path
+            if (st == LT_OK) info_host[7] = n_fixed;      // incidences re-evaluated in float64 (a ReLU within reach of a switch)
         }
     }
     lt_plan_destroy(plan, stream);

@@ -5,6 +5,7 @@
 // algo 1: fp32 SIMT, 128x64x32 tiles, 8x4 register blocking, register-staged double buffering.
 // algo 2: 3xTF32 on the 5th-gen tensor cores (tcgen05.mma kind::tf32, TMEM accumulators) — see
 //         gemm_tc.cu.  algo 0 (auto) picks it for products above 2^24 multiply-adds with N ≥ 16.
+// algo 3: float64 accumulation of the float32 products (k_gemm_f64acc), for the rows whose values must be exact.
 #include "common.cuh"
 
 namespace lt {
@@ -118,10 +119,72 @@ k_gemm_simt(const float* __restrict__ A, int64_t lda, const int32_t* __restrict_
     }
 }
 
+// algo 3: float32 operands, products and sums carried in float64, one rounding at the end.  For the few rows whose VALUES
+// enter the result directly — P_v = X[v]·W1 of the perturbed nodes (ΔR = Â[r,v]·P[v] on the active units): the 3xTF32 /
+// float32-accumulate error grows linearly with K (4e-5 of the row scale at K = 3170, profiles/h_error_probe.py), which
+// cancellation between frontier rows amplified to 2.7e-3 on single influence entries of the twitch-shaped config.
+constexpr int GD_ROWS = 8, GD_COLS = 64, GD_KG = 4, GD_KC = 256, GD_THREADS = GD_COLS * GD_KG;
+
+// A CTA owns 8 rows x 64 columns; its 256 threads are 64 columns x 4 k-groups (k ≡ group mod 4), whose partial sums are
+// added in group order at the end — deterministic, and 4x the CTAs and a quarter of the dependent FMA chain of a plain
+// thread-per-column kernel (M = 500, K = 3170: 0.72 ms → tens of µs).
+__global__ void __launch_bounds__(GD_THREADS)
+k_gemm_f64acc(const float* __restrict__ A, int64_t lda, const int32_t* __restrict__ a_rows, const float* __restrict__ B,
+              int64_t ldb, const float* __restrict__ bias, int relu, float* __restrict__ C, int64_t ldc, int M, int N, int K) {
+    __shared__ double As[GD_ROWS][GD_KC];
+    __shared__ double Ps[GD_KG][GD_ROWS][GD_COLS];
+    const int tid = threadIdx.x;
+    const int col = tid % GD_COLS, kg = tid / GD_COLS;
+    const int m0 = blockIdx.y * GD_ROWS, nn = blockIdx.x * GD_COLS + col;
+    double acc[GD_ROWS];
+#pragma unroll
+    for (int r = 0; r < GD_ROWS; ++r) acc[r] = 0.0;
+    for (int k0 = 0; k0 < K; k0 += GD_KC) {
+        for (int idx = tid; idx < GD_ROWS * GD_KC; idx += GD_THREADS) {
+            const int r = idx / GD_KC, kk = idx % GD_KC;
+            const int m = m0 + r, k = k0 + kk;
+            As[r][kk] = (m < M && k < K) ? (double)__ldg(A + (int64_t)(a_rows ? a_rows[m] : m) * lda + k) : 0.0;
+        }
+        __syncthreads();
+        if (nn < N) {
+            const int kend = min(GD_KC, K - k0);
+#pragma unroll 4
+            for (int kk = kg; kk < kend; kk += GD_KG) {
+                const double b = (double)__ldg(B + (int64_t)(k0 + kk) * ldb + nn);
+#pragma unroll
+                for (int r = 0; r < GD_ROWS; ++r) acc[r] = fma(As[r][kk], b, acc[r]);
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int r = 0; r < GD_ROWS; ++r) Ps[kg][r][col] = acc[r];
+    __syncthreads();
+    if (kg != 0 || nn >= N) return;
+#pragma unroll
+    for (int r = 0; r < GD_ROWS; ++r) {
+        const int m = m0 + r;
+        if (m >= M) break;
+        double sum = Ps[0][r][col];
+#pragma unroll
+        for (int q = 1; q < GD_KG; ++q) sum += Ps[q][r][col];
+        float v = (float)(bias ? sum + (double)__ldg(bias + nn) : sum);
+        if (relu) v = fmaxf(v, 0.f);
+        C[(int64_t)m * ldc + nn] = v;
+    }
+}
+
 int gemm_f32(const float* A, int64_t lda, const int32_t* a_rows, const float* B, int64_t ldb, int transB,
              const float* bias, int relu, float* C, int64_t ldc, int32_t M, int32_t N, int32_t K, int algo,
              cudaStream_t s) {
     if (M == 0 || N == 0) return LT_OK;
+    if (algo == 3) {
+        if (transB) { set_error("lt_gemm_f32: algo=3 (float64 accumulation) does not take a transposed B"); return LT_ERR_ARG; }
+        dim3 grid((unsigned)ceil_div(N, GD_COLS), (unsigned)ceil_div(M, GD_ROWS));
+        k_gemm_f64acc<<<grid, GD_THREADS, 0, s>>>(A, lda, a_rows, B, ldb, bias, relu, C, ldc, M, N, K);
+        LT_LAUNCH_CHECK();
+        return LT_OK;
+    }
     if (algo == 0 || algo == 2) {
         bool handled = false;
         LT_TRY(gemm_3xtf32(A, lda, a_rows, B, ldb, transB, bias, relu, C, ldc, M, N, K, s, algo == 2, &handled));
@@ -148,6 +211,6 @@ extern "C" int lt_gemm_f32(const float* A, int64_t lda, const int32_t* a_rows, c
                            int32_t K, int algo, lt_stream_t stream) {
     LT_CHECK_ARG(A && B && C && M >= 0 && N >= 0 && K >= 0 && lda >= K && ldc >= N, "lt_gemm_f32");
     LT_CHECK_ARG(transB ? ldb >= K : ldb >= N, "lt_gemm_f32: ldb");
-    LT_CHECK_ARG(algo >= 0 && algo <= 2, "lt_gemm_f32: algo");
+    LT_CHECK_ARG(algo >= 0 && algo <= 3, "lt_gemm_f32: algo");
     return lt::gemm_f32(A, lda, a_rows, B, ldb, transB, bias, relu, C, ldc, M, N, K, algo, (cudaStream_t)stream);
 }

@@ -316,19 +316,21 @@ k_gemm_tc(Prod prod, const uint32_t* __restrict__ Bimg, const float* __restrict_
                     if (EPI == TC_EPI_SIGN) {
                         // lane = row: its 32 columns make exactly one word of the row's sign mask
                         uint32_t word = 0;
-                        float mn = __uint_as_float(0x7f7f7f7fu);
+                        float mn = __uint_as_float(0x7f7f7f7fu), mx = 0.f;
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             const float x = __uint_as_float(v[j]) + bias_s[c0 + j];
                             if (j < lim && n0 + c0 + j < N) {
                                 word |= (x > 0.f ? 1u : 0u) << j;
                                 mn = fminf(mn, fabsf(x));
+                                mx = fmaxf(mx, fabsf(x));
                             }
                         }
                         const int m = m_base + lane;
                         if (m < M && n0 + c0 < N) {
                             sign_words[(int64_t)m * words_per_row + ((n0 + c0) >> 5)] = word;
                             atomicMin(minabs_bits + m, __float_as_uint(mn));
+                            atomicMax(minabs_bits + M + m, __float_as_uint(mx));    // [M, 2M): the row's largest magnitude
                         }
                     } else {
 #pragma unroll
@@ -412,7 +414,8 @@ static inline int tc_pick_nt(int N) {
 }
 
 int tc_prepack_b(const float* B, int64_t ldb, int transB, int32_t N, int32_t K, int32_t n_pad, uint32_t* img, cudaStream_t s);
-// signs of A[M,K]·B + bias: sign_words [M, (N+31)/32] and minabs_bits [M] (caller pre-sets them to 0x7f7f7f7f); gemm_tc.cu
+// signs of A[M,K]·B + bias: sign_words [M, (N+31)/32] and minabs_bits [2M]: [0,M) the row's smallest |value| (caller pre-sets
+// 0x7f7f7f7f), [M,2M) its largest (caller pre-sets 0); gemm_tc.cu
 int gemm_3xtf32_signs(const float* A, int64_t lda, const float* B, int64_t ldb, const float* bias, int32_t M, int32_t N,
                       int32_t K, uint32_t* sign_words, uint32_t* minabs_bits, cudaStream_t s);
 

@@ -201,19 +201,21 @@ k_gemm_ws(Prod prod, const uint32_t* __restrict__ Bimg, const float* __restrict_
                 const int lim = min(NT - c0, 32);
                 if (EPI == TC_EPI_SIGN) {
                     uint32_t word = 0;
-                    float mn = __uint_as_float(0x7f7f7f7fu);
+                    float mn = __uint_as_float(0x7f7f7f7fu), mx = 0.f;
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         const float x = __uint_as_float(v[j]) + bias_s[c0 + j];
                         if (j < lim && n0 + c0 + j < N) {
                             word |= (x > 0.f ? 1u : 0u) << j;
                             mn = fminf(mn, fabsf(x));
+                                mx = fmaxf(mx, fabsf(x));
                         }
                     }
                     const int m = m_base + lane;
                     if (m < M && n0 + c0 < N) {
                         sign_words[(int64_t)m * words_per_row + ((n0 + c0) >> 5)] = word;
                         atomicMin(minabs_bits + m, __float_as_uint(mn));
+                            atomicMax(minabs_bits + M + m, __float_as_uint(mx));    // [M, 2M): the row's largest magnitude
                     }
                 } else {
 #pragma unroll

@@ -17,7 +17,9 @@ const OptDef kOpts[OPT_COUNT] = {
     {"overlap", "LT_NO_OVERLAP", 1, true},          {"sign_path", "LT_NO_SIGN_PATH", 1, true},
     {"tc_ws", "LT_TC_WS", 1, false},                {"spmm_panel", "LT_SPMM_PANEL", 0, false},
     {"spmm_panel_mb", "LT_SPMM_PANEL_MB", 48, false}, {"spmm_panel_lmin", "LT_SPMM_PANEL_LMIN", 64, false},
-    {"spmm_hub", "LT_SPMM_HUB", 1, false},          {"spmm_hub_mb", "LT_SPMM_HUB_MB", 64, false},
+    {"spmm_hub", "LT_SPMM_HUB", 0, false},          {"spmm_hub_mb", "LT_SPMM_HUB_MB", 64, false},
+    {"fix_eps", "LT_FIX_EPS", 19, false},           {"spmm_stage", "LT_SPMM_STAGE", 0, false},
+    {"spmm_segmeta", "LT_SPMM_SEGMETA", 1, false},
 };
 std::atomic<int> g_opt[OPT_COUNT];
 std::once_flag g_opt_once;

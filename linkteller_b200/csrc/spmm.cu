@@ -9,6 +9,9 @@
 #include "common.cuh"
 
 #include <stdlib.h>
+#include <string.h>
+
+#include <mutex>
 
 namespace lt {
 
@@ -33,29 +36,67 @@ __global__ void k_spmm_segcount(const int32_t* __restrict__ indptr, const int32_
 }
 
 
+// seg_meta[g] = {first entry, one past the last entry, output position il, segments of the row}: a warp of the product
+// reads its work item in ONE load instead of a 19-step binary search over seg_off followed by rows[] and indptr[]
+// (four dependent round trips before the first gather on a kernel that is bound by latency x bytes in flight).
+__global__ void k_spmm_segmeta(const int32_t* __restrict__ indptr, const int32_t* __restrict__ rows, const int32_t* __restrict__ sel,
+                               int32_t n_rows, const int32_t* __restrict__ seg_off, int4* __restrict__ seg_meta) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_rows) return;
+    const int32_t il = list_pos(sel, i);
+    const int32_t r = rows ? rows[il] : il;
+    const int32_t beg = indptr[r], end = indptr[r + 1];
+    const int32_t first = seg_off[i], nseg = seg_off[i + 1] - first;
+    for (int32_t k = 0; k < nseg; ++k)
+        seg_meta[first + k] = make_int4(beg + k * SPMM_SEG, min(end, beg + (k + 1) * SPMM_SEG), il, nseg);
+}
+
 // NV = float4 slices per lane (d ≤ 128·NV).  seg_off: exclusive scan of nseg (n_rows+1 entries).
 // The (column, value) pairs of the NEXT 32 non-zeros are loaded before the gathers of the current 32 are
 // issued, so a warp never waits for an index load with nothing else in flight.  Lanes keep the float4
 // index of "their" B row (32 bits — the host checks n_cols·ldb4 < 2³²), so one gather costs a shuffle,
 // a wide multiply-add and the load.
-template <int NV, int GIF, int MINB>   // GIF = gathers in flight per lane, MINB = resident CTAs per SM asked of ptxas
+// HUB: the most-gathered rows of B (the highest-degree columns) live in a compact copy `Hub4` that the launch keeps
+// resident in the L2 (persisting access-policy window, see HubPanel below); a column c is a hub iff bit c of hub_bits is
+// set and its slot is hub_pref[c / 32] + popcount of the lower bits.  Offsets carry the choice in their top bit.
+constexpr uint32_t HUB_FLAG = 0x80000000u;
+
+template <bool HUB>
+__device__ __forceinline__ uint32_t spmm_offset(int32_t c, uint32_t ldb4, const HubView& hub) {
+    if (HUB) {
+        const uint32_t b = hub.bits[c >> 5], m = 1u << (c & 31);
+        if (b & m) return HUB_FLAG | ((uint32_t)(hub.pref[c >> 5] + __popc(b & (m - 1))) * hub.ld4);
+    }
+    return (uint32_t)c * ldb4;
+}
+
+__device__ __forceinline__ int32_t seg_meta_total(const int32_t* __restrict__ seg_off, int32_t n_rows) { return __ldg(seg_off + n_rows); }
+
+template <int NV, int GIF, int MINB, bool HUB>   // GIF = gathers in flight per lane, MINB = resident CTAs per SM asked of ptxas
 __global__ void __launch_bounds__(SPMM_THREADS, MINB)
 k_spmm_vec(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices, const float* __restrict__ values,
            const int32_t* __restrict__ rows, const int32_t* __restrict__ sel, int32_t n_rows, const int32_t* __restrict__ seg_off,
            const float4* __restrict__ B4, uint32_t ldb4, int32_t d4, const float* __restrict__ bias, int relu,
-           float* __restrict__ C, int64_t ldc, float* __restrict__ partial) {
+           float* __restrict__ C, int64_t ldc, float* __restrict__ partial, HubView hub, const int4* __restrict__ seg_meta) {
     const int lane = threadIdx.x & 31;
     const int64_t g = ((int64_t)blockIdx.x * SPMM_THREADS + threadIdx.x) >> 5;
-    const int32_t total = seg_off[n_rows];
-    if (g >= total) return;
-    const int32_t i = (int32_t)upper_bound(seg_off, 0, (int64_t)n_rows + 1, (int32_t)g) - 1;
-    const int32_t il = list_pos(sel, i);
-    const int32_t r = rows ? rows[il] : il;
-    const int32_t first = seg_off[i];
-    const int32_t nseg = seg_off[i + 1] - first;
-    const int32_t row_beg = indptr[r], row_end = indptr[r + 1];
-    const int32_t s0 = row_beg + ((int32_t)g - first) * SPMM_SEG;
-    const int32_t s1 = min(row_end, s0 + SPMM_SEG);
+    int32_t s0, s1, il, nseg;
+    if (seg_meta) {
+        if (g >= seg_meta_total(seg_off, n_rows)) return;
+        const int4 m = __ldg(seg_meta + g);
+        s0 = m.x; s1 = m.y; il = m.z; nseg = m.w;
+    } else {
+        const int32_t total = seg_off[n_rows];
+        if (g >= total) return;
+        const int32_t i = (int32_t)upper_bound(seg_off, 0, (int64_t)n_rows + 1, (int32_t)g) - 1;
+        il = list_pos(sel, i);
+        const int32_t r = rows ? rows[il] : il;
+        const int32_t first = seg_off[i];
+        nseg = seg_off[i + 1] - first;
+        const int32_t row_beg = indptr[r], row_end = indptr[r + 1];
+        s0 = row_beg + ((int32_t)g - first) * SPMM_SEG;
+        s1 = min(row_end, s0 + SPMM_SEG);
+    }
 
     float4 acc[NV];
 #pragma unroll
@@ -66,12 +107,13 @@ k_spmm_vec(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indic
     const float4* Bl[NV];
 #pragma unroll
     for (int q = 0; q < NV; ++q) Bl[q] = B4 + min(lane + 32 * q, d4 - 1);
+    const float4* Hl = HUB ? hub.rows4 + min(lane, d4 - 1) : nullptr;       // HUB ⇒ NV == 1
 
-    uint32_t mo = s0 + lane < s1 ? (uint32_t)indices[s0 + lane] * ldb4 : 0u;
+    uint32_t mo = s0 + lane < s1 ? spmm_offset<HUB>(indices[s0 + lane], ldb4, hub) : 0u;
     float mv = s0 + lane < s1 ? values[s0 + lane] : 0.f;
     for (int32_t base = s0; base < s1; base += 32) {
         const int32_t nx = base + 32 + lane;
-        const uint32_t no = nx < s1 ? (uint32_t)indices[nx] * ldb4 : 0u;
+        const uint32_t no = nx < s1 ? spmm_offset<HUB>(indices[nx], ldb4, hub) : 0u;
         const float nv = nx < s1 ? values[nx] : 0.f;
         const int cnt = min(32, s1 - base);
         for (int k = 0; k < cnt; k += GIF) {
@@ -81,8 +123,12 @@ k_spmm_vec(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indic
 #pragma unroll
             for (int u = 0; u < GIF; ++u) {
                 const uint32_t o = __shfl_sync(LT_FULL, mo, (k + u) & 31);
+                if (HUB) {
+                    x[u][0] = __ldg(((o & HUB_FLAG) ? Hl : Bl[0]) + (o & ~HUB_FLAG));
+                } else {
 #pragma unroll
-                for (int q = 0; q < NV; ++q) x[u][q] = __ldg(Bl[q] + o);
+                    for (int q = 0; q < NV; ++q) x[u][q] = __ldg(Bl[q] + o);
+                }
             }
 #pragma unroll
             for (int u = 0; u < GIF; ++u) {
@@ -119,6 +165,99 @@ k_spmm_vec(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indic
             const int col = lane + 32 * q;
             if (col < d4) dst[col] = acc[q];
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------ shared-memory staged variant
+// k_spmm_vec keeps its gathers in registers: 8 rows of B in flight per lane, 24 warps per SM, and every batch of 8 ends
+// in a full memory round trip before the next one is issued (ncu r2d: long_scoreboard 13 stalls per issue, DRAM 72 %
+// busy, and 15 % fewer DRAM bytes — the hub panel — buy no time: the kernel is bound by latency x bytes in flight, not
+// by bandwidth).  Here a warp streams the rows of B it needs through a ring of STG_RING slots in shared memory with
+// cp.async (16 bytes per lane, L1 bypassed): the copy of entry e + STG_RING is issued the moment entry e has been
+// consumed, so 32 rows (12.8 KB at d = 100) are in flight per warp at all times and 16 warps fill the SM's shared memory
+// — 2.7x the bytes in flight of the register version.  Indices are fetched two chunks ahead (the hub translation of a
+// chunk needs its own round trip).  Same FMAs in the same order as k_spmm_vec: the results are bit-identical.
+constexpr int STG_RING = 32;
+constexpr int STG_WARPS = 4;
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    const uint32_t sa = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <bool HUB>
+__global__ void __launch_bounds__(32 * STG_WARPS, 4)
+k_spmm_stage(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices, const float* __restrict__ values,
+             const int32_t* __restrict__ rows, const int32_t* __restrict__ sel, int32_t n_rows, const int32_t* __restrict__ seg_off,
+             const float4* __restrict__ B4, uint32_t ldb4, int32_t d4, const float* __restrict__ bias, int relu,
+             float* __restrict__ C, int64_t ldc, float* __restrict__ partial, HubView hub) {
+    extern __shared__ float4 stage[];                                     // [STG_WARPS][STG_RING][d4]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t g = (int64_t)blockIdx.x * STG_WARPS + warp;
+    const int32_t total = seg_off[n_rows];
+    if (g >= total) return;
+    const int32_t i = (int32_t)upper_bound(seg_off, 0, (int64_t)n_rows + 1, (int32_t)g) - 1;
+    const int32_t il = list_pos(sel, i);
+    const int32_t r = rows ? rows[il] : il;
+    const int32_t first = seg_off[i];
+    const int32_t nseg = seg_off[i + 1] - first;
+    const int32_t row_beg = indptr[r], row_end = indptr[r + 1];
+    const int32_t s0 = row_beg + ((int32_t)g - first) * SPMM_SEG;
+    const int32_t s1 = min(row_end, s0 + SPMM_SEG);
+    float4* ring = stage + (size_t)warp * STG_RING * d4;
+    const bool active = lane < d4;
+    const float4* Bl = B4 + lane;
+    const float4* Hl = HUB ? hub.rows4 + lane : nullptr;
+
+    auto load_off = [&](int32_t pos) -> uint32_t { return pos < s1 ? spmm_offset<HUB>(indices[pos], ldb4, hub) : 0u; };
+    auto issue = [&](uint32_t o, int slot, bool live) {                  // one row of B → ring[slot]; always one group
+        if (live && active) {
+            const float4* src = (HUB && (o & HUB_FLAG)) ? Hl + (o & ~HUB_FLAG) : Bl + o;
+            cp_async16(ring + (size_t)slot * d4 + lane, src);
+        }
+        cp_async_commit();
+    };
+
+    // offsets of the current chunk, the next one and the one after; values of the current and the next chunk
+    uint32_t o0 = load_off(s0 + lane), o1 = load_off(s0 + 32 + lane), o2 = load_off(s0 + 64 + lane);
+    float v0 = s0 + lane < s1 ? values[s0 + lane] : 0.f;
+    float v1 = s0 + 32 + lane < s1 ? values[s0 + 32 + lane] : 0.f;
+    // prologue: the first STG_RING entries (= the first chunk)
+#pragma unroll 8
+    for (int k = 0; k < STG_RING; ++k) issue(__shfl_sync(LT_FULL, o0, k), k, s0 + k < s1);
+
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int32_t base = s0; base < s1; base += 32) {
+        const int cnt = min(32, s1 - base);
+#pragma unroll 4
+        for (int k = 0; k < 32; ++k) {
+            if (k >= cnt) { cp_async_commit(); continue; }               // warp-uniform; keeps one group per step
+            cp_async_wait<STG_RING - 1>();                                // the oldest pending row (this entry) has landed
+            __syncwarp();
+            const float v = __shfl_sync(LT_FULL, v0, k);
+            if (active) fma4(acc, v, ring[(size_t)k * d4 + lane]);
+            __syncwarp();                                                 // slot k is free again
+            issue(__shfl_sync(LT_FULL, o1, k), k, base + 32 + k < s1);    // entry of the next chunk into the same slot
+        }
+        o0 = o1; o1 = o2; v0 = v1;
+        o2 = load_off(base + 96 + lane);
+        v1 = base + 64 + lane < s1 ? values[base + 64 + lane] : 0.f;
+    }
+    cp_async_wait<0>();
+
+    if (!active) return;
+    if (nseg == 1) {
+        if (bias) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(bias) + lane);
+            acc.x += b.x; acc.y += b.y; acc.z += b.z; acc.w += b.w;
+        }
+        if (relu) { acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f); }
+        reinterpret_cast<float4*>(C + (int64_t)il * ldc)[lane] = acc;
+    } else {
+        (reinterpret_cast<float4*>(partial) + (int64_t)g * d4)[lane] = acc;
     }
 }
 
@@ -395,12 +534,160 @@ k_spmm_scalar(const int32_t* __restrict__ indptr, const int32_t* __restrict__ in
     }
 }
 
+// ------------------------------------------------------------------------------------ hub panel (L2-resident hot rows of B)
+// A restricted product Â[R,:]·B on a graph whose B does not fit the L2 re-fetches every gathered row from DRAM: on C5
+// 13.9 GB of traffic for 1.4 GB of compulsory bytes (ncu r1k).  Gathers are not uniform: column c is gathered in
+// proportion to its degree, and on a scale-free graph the K highest-degree columns take ~√(K/n) of all gathers (C5:
+// K = 200 K rows = 76 MB → 28.6 %, measured from the CSR).  hub_prepare() copies those rows into one contiguous panel
+// (rows padded to whole 32-byte sectors) and describes membership by a bitmap + popcount prefix (612 KB for 2.45 M
+// nodes); the SpMM launch then runs under a persisting access-policy window over the panel, so hub gathers hit the L2's
+// set-aside region whatever the streaming tail does to the rest of the cache.  The degree threshold is chosen on the
+// device from a degree histogram (no host sync); the sum of a row is taken in the same order as without the panel, so
+// the result is bit-identical.
+constexpr int HUB_BINS = 4096;
+
+__global__ void __launch_bounds__(256)
+k_hub_hist(const int32_t* __restrict__ indptr, int32_t n, int32_t* __restrict__ hist) {
+    __shared__ int32_t sh[HUB_BINS];
+    for (int i = threadIdx.x; i < HUB_BINS; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x)
+        atomicAdd(&sh[min(indptr[r + 1] - indptr[r], HUB_BINS - 1)], 1);
+    __syncthreads();
+    for (int i = threadIdx.x; i < HUB_BINS; i += blockDim.x)
+        if (sh[i]) atomicAdd(&hist[i], sh[i]);
+}
+// thr[0] = smallest degree d with #{deg ≥ d} ≤ kmax (single thread: 4096 bins)
+__global__ void k_hub_pick(const int32_t* __restrict__ hist, int32_t kmax, int32_t* __restrict__ thr) {
+    if (threadIdx.x || blockIdx.x) return;
+    int64_t acc = 0;
+    int d = HUB_BINS;
+    while (d > 1 && acc + hist[d - 1] <= kmax) { acc += hist[d - 1]; --d; }
+    thr[0] = d;            // d == HUB_BINS: not even the top bin fits — no hubs
+}
+// warp per 32 nodes: membership word + its popcount
+__global__ void __launch_bounds__(256)
+k_hub_bits(const int32_t* __restrict__ indptr, int32_t n, const int32_t* __restrict__ thr, uint32_t* __restrict__ bits,
+           int32_t* __restrict__ cnt, int32_t n_words) {
+    const int lane = threadIdx.x & 31;
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (w >= n_words) return;
+    const int64_t r = w * 32 + lane;
+    const int32_t d0 = thr[0];
+    const bool hub = r < n && d0 < HUB_BINS && indptr[r + 1] - indptr[r] >= d0;
+    const uint32_t b = __ballot_sync(LT_FULL, hub);
+    if (lane == 0) { bits[w] = b; cnt[w] = __popc(b); }
+}
+// warp per word: copy its hub rows into their slots
+__global__ void __launch_bounds__(256)
+k_hub_copy(const uint32_t* __restrict__ bits, const int32_t* __restrict__ pref, int32_t n_words, const float4* __restrict__ B4,
+           uint32_t ldb4, int32_t d4, float4* __restrict__ hub4, uint32_t ldh4) {
+    const int lane = threadIdx.x & 31;
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (w >= n_words) return;
+    uint32_t b = bits[w];
+    int32_t slot = pref[w];
+    while (b) {
+        const int bit = __ffs(b) - 1;
+        b &= b - 1;
+        const float4* src = B4 + (uint64_t)(w * 32 + bit) * ldb4;
+        float4* dst = hub4 + (uint64_t)slot * ldh4;
+        for (int q = lane; q < d4; q += 32) dst[q] = __ldg(src + q);
+        ++slot;
+    }
+}
+
+namespace {
+struct HubStore { void* ptr = nullptr; size_t bytes = 0; bool limit_set = false; };
+HubStore g_hub[64];
+std::mutex g_hub_mu;
+}  // namespace
+
+// worth it only when B is far beyond the L2 and the vector kernel with one float4 per lane applies
+bool hub_applicable(int32_t n_cols, int64_t ldb, int32_t d, const float* B) {
+    return opt(OPT_SPMM_HUB) != 0 && d % 4 == 0 && d <= 128 && ldb % 4 == 0 && (uintptr_t)B % 16 == 0 &&
+           (int64_t)n_cols * d * 4 >= ((int64_t)256 << 20) && (int64_t)n_cols * (ldb / 4) < ((int64_t)1 << 31);
+}
+
+// Builds the panel for B on stream s.  bits / pref live in `scratch` (they must outlive the product); the panel rows live
+// in a per-device buffer the library keeps (the second persistent allocation besides lt_plan: the persisting L2 lines
+// must keep their address from one attack to the next, or stale lines would occupy the set-aside region).
+int hub_prepare(const int32_t* indptr, int32_t n, const float* B, int64_t ldb, int32_t d, HubPanel* out, Scratch& scratch,
+                cudaStream_t s) {
+    out->valid = false;
+    int dev = 0;
+    LT_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return LT_OK;
+    int max_persist = 0, max_window = 0;
+    cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+    cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+    size_t cap = (size_t)opt(OPT_SPMM_HUB_MB) << 20;
+    if ((size_t)max_persist < cap) cap = (size_t)max_persist;
+    if ((size_t)max_window < cap) cap = (size_t)max_window;
+    const int32_t d4 = d / 4;
+    const uint32_t ldh4 = (uint32_t)((d4 + 1) & ~1);             // whole 32-byte sectors per row
+    const int64_t kmax = (int64_t)(cap / ((size_t)ldh4 * 16));
+    if (kmax < 1024) return LT_OK;                                // no set-aside L2 on this device / option set to 0
+    void* panel = nullptr;
+    {
+        std::lock_guard<std::mutex> lock(g_hub_mu);
+        HubStore& st = g_hub[dev];
+        if (st.bytes < cap) {
+            if (st.ptr) cudaFree(st.ptr);
+            st.ptr = nullptr; st.bytes = 0;
+            if (cudaMalloc(&st.ptr, cap) != cudaSuccess) { cudaGetLastError(); return LT_OK; }   // no panel: plain product
+            st.bytes = cap;
+            st.limit_set = false;
+        }
+        if (!st.limit_set) {
+            if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, cap) != cudaSuccess) { cudaGetLastError(); return LT_OK; }
+            st.limit_set = true;
+        }
+        panel = st.ptr;
+    }
+    const int32_t n_words = (n + 31) / 32;
+    int32_t *hist, *thr, *cnt, *pref;
+    uint32_t* bits;
+    LT_TRY(scratch.alloc(&hist, (size_t)HUB_BINS + 1));
+    LT_TRY(scratch.alloc(&bits, (size_t)n_words));
+    LT_TRY(scratch.alloc(&cnt, (size_t)n_words + 1));
+    LT_TRY(scratch.alloc(&pref, (size_t)n_words + 1));
+    thr = hist + HUB_BINS;
+    if (s != scratch.stream) {        // runs on another stream than the one that owns the scratch (and the inputs): order after it
+        cudaEvent_t ev;
+        LT_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        const cudaError_t e1 = cudaEventRecord(ev, scratch.stream);
+        const cudaError_t e2 = e1 == cudaSuccess ? cudaStreamWaitEvent(s, ev, 0) : e1;
+        cudaEventDestroy(ev);
+        if (e2 != cudaSuccess) { set_error("hub_prepare: fork failed: %s", cudaGetErrorString(e2)); return LT_ERR_CUDA; }
+    }
+    ProfScope prof("spmm_hub_prepare", s);
+    LT_CUDA(cudaMemsetAsync(hist, 0, ((size_t)HUB_BINS + 1) * 4, s));
+    k_hub_hist<<<(unsigned)num_sms() * 4, 256, 0, s>>>(indptr, n, hist);
+    LT_LAUNCH_CHECK();
+    k_hub_pick<<<1, 32, 0, s>>>(hist, (int32_t)(kmax > n ? n : kmax), thr);
+    LT_LAUNCH_CHECK();
+    k_hub_bits<<<(unsigned)ceil_div((int64_t)n_words * 32, 256), 256, 0, s>>>(indptr, n, thr, bits, cnt, n_words);
+    LT_LAUNCH_CHECK();
+    LT_TRY(exclusive_scan_i32(cnt, pref, n_words, s));
+    k_hub_copy<<<(unsigned)ceil_div((int64_t)n_words * 32, 256), 256, 0, s>>>(bits, pref, n_words, reinterpret_cast<const float4*>(B),
+                                                                           (uint32_t)(ldb / 4), d4, reinterpret_cast<float4*>(panel), ldh4);
+    LT_LAUNCH_CHECK();
+    out->view = HubView{bits, pref, reinterpret_cast<const float4*>(panel), ldh4};
+    out->base = panel;
+    out->bytes = (size_t)kmax * ldh4 * 16;
+    out->valid = true;
+    return LT_OK;
+}
+
 // seg_off_known / total_seg_known (optional): exclusive scan of the per-row segment counts (n_rows+1 entries,
 // SPMM_SEG non-zeros per segment, at least one per row) and its total, when the caller already has them — the
 // attack plan does — so that the product needs neither the counting pass nor its host synchronisation.
+// hub (optional): a panel built by hub_prepare() for this B; used by the plain pass of the one-float4-per-lane kernel.
 int spmm_csr_f32_seg(const int32_t* indptr, const int32_t* indices, const float* values, int32_t n_cols,
                      const int32_t* rows, int32_t n_rows, const float* B, int64_t ldb, int32_t d, const float* bias, int relu,
-                     float* C, int64_t ldc, const int32_t* seg_off_known, int64_t total_seg_known, cudaStream_t s);
+                     float* C, int64_t ldc, const int32_t* seg_off_known, int64_t total_seg_known, cudaStream_t s,
+                     const HubPanel* hub = nullptr);
 
 int spmm_csr_f32(const int32_t* indptr, const int32_t* indices, const float* values, int32_t n_cols,
                  const int32_t* rows, int32_t n_rows, const float* B, int64_t ldb, int32_t d, const float* bias, int relu,
@@ -410,7 +697,8 @@ int spmm_csr_f32(const int32_t* indptr, const int32_t* indices, const float* val
 
 int spmm_csr_f32_seg(const int32_t* indptr, const int32_t* indices, const float* values, int32_t n_cols,
                      const int32_t* rows, int32_t n_rows, const float* B, int64_t ldb, int32_t d, const float* bias, int relu,
-                     float* C, int64_t ldc, const int32_t* seg_off_known, int64_t total_seg_known, cudaStream_t s) {
+                     float* C, int64_t ldc, const int32_t* seg_off_known, int64_t total_seg_known, cudaStream_t s,
+                     const HubPanel* hub) {
     if (n_rows == 0 || d == 0) return LT_OK;
     const bool vec = (d % 4 == 0) && (ldb % 4 == 0) && (ldc % 4 == 0) && d <= 512 && (int64_t)n_cols * (ldb / 4) < ((int64_t)1 << 32) &&
                      ((uintptr_t)B % 16 == 0) && ((uintptr_t)C % 16 == 0) && (!bias || (uintptr_t)bias % 16 == 0);
@@ -449,10 +737,56 @@ int spmm_csr_f32_seg(const int32_t* indptr, const int32_t* indices, const float*
         const bool multi = total_seg > n_list;
         if (multi) LT_TRY(scratch.alloc(&partial, (size_t)total_seg * d));
         const unsigned bl = (unsigned)ceil_div(total_seg * 32, SPMM_THREADS);
-#define LT_SPMM_V(NV_, GIF_, MINB_) k_spmm_vec<NV_, GIF_, MINB_><<<bl, SPMM_THREADS, 0, s>>>(indptr, indices, values, rows, sel, n_list, seg_off, B4, (uint32_t)(ldb / 4), d4, bias, relu, C, ldc, partial)
+        int4* seg_meta = nullptr;
+        if (opt(OPT_SPMM_SEGMETA) != 0 && total_seg >= (int64_t)num_sms() * 64) {     // big products: one load per work item
+            LT_TRY(scratch.alloc(&seg_meta, (size_t)total_seg));
+            k_spmm_segmeta<<<(unsigned)ceil_div(n_list, 256), 256, 0, s>>>(indptr, rows, sel, n_list, seg_off, seg_meta);
+            LT_LAUNCH_CHECK();
+        }
+#define LT_SPMM_V(NV_, GIF_, MINB_) k_spmm_vec<NV_, GIF_, MINB_, false><<<bl, SPMM_THREADS, 0, s>>>(indptr, indices, values, rows, sel, n_list, seg_off, B4, (uint32_t)(ldb / 4), d4, bias, relu, C, ldc, partial, HubView{nullptr, nullptr, nullptr, 0}, seg_meta)
         // d ≤ 128: 8 gathers in flight per lane at 3 CTAs/SM (no spills) measured best on C5 (2.54 ms; 4 CTAs 2.64,
         // 16 in flight at 2 CTAs 3.16): the kernel then moves its 13.9 GB of DRAM traffic at 84 % of the copy peak
-        if (d4 <= 32) LT_SPMM_V(1, 8, 3);
+        const bool use_hub = d4 <= 32 && hub && hub->valid;
+        if (d4 <= 32 && opt(OPT_SPMM_STAGE) != 0 && total_seg >= (int64_t)num_sms() * 64) {
+            const size_t smem = (size_t)STG_WARPS * STG_RING * d4 * sizeof(float4);
+            const unsigned bls = (unsigned)ceil_div(total_seg, STG_WARPS);
+            cudaStreamAttrValue attr;
+            memset(&attr, 0, sizeof(attr));
+            if (use_hub) {
+                attr.accessPolicyWindow.base_ptr = hub->base;
+                attr.accessPolicyWindow.num_bytes = hub->bytes;
+                attr.accessPolicyWindow.hitRatio = 1.0f;
+                attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+                attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+                LT_CUDA(cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &attr));
+                LT_CUDA(cudaFuncSetAttribute(k_spmm_stage<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                k_spmm_stage<true><<<bls, 32 * STG_WARPS, smem, s>>>(indptr, indices, values, rows, sel, n_list, seg_off, B4,
+                                                                     (uint32_t)(ldb / 4), d4, bias, relu, C, ldc, partial, hub->view);
+                attr.accessPolicyWindow.num_bytes = 0;
+                cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &attr);
+            } else {
+                LT_CUDA(cudaFuncSetAttribute(k_spmm_stage<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                k_spmm_stage<false><<<bls, 32 * STG_WARPS, smem, s>>>(indptr, indices, values, rows, sel, n_list, seg_off, B4,
+                                                                      (uint32_t)(ldb / 4), d4, bias, relu, C, ldc, partial,
+                                                                      HubView{nullptr, nullptr, nullptr, 0});
+            }
+        }
+        else if (use_hub) {
+            // hub gathers under a persisting window over the panel; everything else streams through the rest of the L2
+            cudaStreamAttrValue attr;
+            memset(&attr, 0, sizeof(attr));
+            attr.accessPolicyWindow.base_ptr = hub->base;
+            attr.accessPolicyWindow.num_bytes = hub->bytes;
+            attr.accessPolicyWindow.hitRatio = 1.0f;
+            attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            LT_CUDA(cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &attr));
+            k_spmm_vec<1, 8, 3, true><<<bl, SPMM_THREADS, 0, s>>>(indptr, indices, values, rows, sel, n_list, seg_off, B4,
+                                                                  (uint32_t)(ldb / 4), d4, bias, relu, C, ldc, partial, hub->view, seg_meta);
+            attr.accessPolicyWindow.num_bytes = 0;                      // the caller's stream gets its default policy back
+            cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &attr);
+        }
+        else if (d4 <= 32) LT_SPMM_V(1, 8, 3);
         else if (d4 <= 64) LT_SPMM_V(2, 4, 4);
         else if (d4 <= 96) LT_SPMM_V(3, 4, 3);
         else LT_SPMM_V(4, 4, 2);

@@ -55,7 +55,8 @@ def test_full_size_config_matches_the_reference_run(golden, case, tmp_path, monk
     n_pairs = int(g["n_pairs"])
     assert np.array_equal(y, np.unpackbits(g["y"])[:n_pairs]) and int(y.sum()) == int(g["n_exist"])
     p32, p64 = g["pred32"].astype(np.float64), g["pred64"]
-    assert np.array_equal(pred == 0, p64 == 0) and np.array_equal(pred == 0, p32 == 0)     # exact zeros, all 124 750 pairs
+    assert np.array_equal(pred == 0, p64 == 0)            # exact zeros = the float64 run's, on all 124 750 pairs
+    assert not ((p32 != 0) & (pred == 0)).any()           # the float32 run may round a tiny difference to 0, never the reverse
     nz = p64 != 0
     rel = np.abs(pred[nz] - p64[nz]) / np.abs(p64[nz])
     rel32 = np.abs(p32[nz] - p64[nz]) / np.abs(p64[nz])

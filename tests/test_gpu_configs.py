@@ -69,13 +69,13 @@ def test_sign_mask_path_matches_value_path_and_oracle(monkeypatch):
         assert info["exact_path_incidences"] >= min_exact
         with ops.option("sign_path", 0):
             b, info_b = ops.attack_efficient(wl.adj_hat, wl.x, wl.w1, wl.b1, wl.w2, wl.test_nodes, wl.delta, want_info=True)
-        assert info_b["exact_path_incidences"] == 0
+        assert info_b["exact_path_incidences"] >= min_exact        # the value path queues the same switching units
         a, b = a.cpu().numpy(), b.cpu().numpy()
         assert np.array_equal(a == 0, b == 0)
         nz = b != 0
         rel = np.abs(a[nz] - b[nz]) / np.abs(b[nz])
         assert rel.max() <= 1e-3, rel.max()   # a switching ReLU contributes −H/δ: two fp32 evaluations of H differ by ~1e-7/δ there
-        if info["exact_path_incidences"] == 0:
+        if info["exact_path_incidences"] == 0 and info_b["exact_path_incidences"] == 0:
             assert np.array_equal(a, b)                 # same A operand, same GEMM: same bits
         check_rows(wl, range(3, 500, 45))               # and the float64 oracle, at this δ
 

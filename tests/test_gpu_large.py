@@ -60,6 +60,30 @@ def test_large_whole_matrix_properties(large):
     assert bool(torch.equal(part, infl[lo:hi]))
 
 
+def test_large_spmm_variants_give_the_same_bits(large):
+    """The restricted SpMM has three opt-in variants kept for the record: hub rows of X gathered from an
+    L2-resident panel under a persisting access-policy window ("spmm_hub"), rows of X staged through shared memory with
+    cp.async ("spmm_stage"), and the work-item table that replaces the binary search ("spmm_segmeta", default on).
+    Every variant sums a row in the same order: switching them must not change a bit of the influence matrix."""
+    from linkteller_b200 import ops
+    wl, infl, info = large
+
+    def run():
+        return ops.attack_efficient(wl.adj_hat, wl.x, wl.w1, wl.b1, wl.w2, wl.test_nodes, wl.delta)
+    with ops.option("spmm_hub", 1), ops.profile() as prof:
+        hub = run()
+    assert "spmm_hub_prepare" in prof.report()
+    with ops.option("spmm_stage", 1):
+        staged = run()
+    with ops.option("spmm_stage", 1), ops.option("spmm_hub", 1):
+        both = run()
+    with ops.option("spmm_segmeta", 0), ops.profile() as prof0:
+        searched = run()
+    assert "spmm_hub_prepare" not in prof0.report()
+    for name, t in (("hub", hub), ("staged", staged), ("hub+staged", both), ("binary search", searched)):
+        assert bool(torch.equal(t, infl)), name
+
+
 def test_reference_arm_inputs_equal_the_product_arm_inputs(large):
     """bench.py --impl reference builds its C5 inputs with torch ops only (oracle/refgen.py) so that it never loads
     the product library; they must be the very arrays the product arm measures."""

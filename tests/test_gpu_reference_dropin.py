@@ -76,7 +76,8 @@ def compare(ref, ours, y64, p64):
     y_r, y_o = np.asarray(d_r["result"]["y"]), np.asarray(d_o["result"]["y"])
     p_r, p_o = np.asarray(d_r["result"]["pred"]), np.asarray(d_o["result"]["pred"])
     assert np.array_equal(y_o, y_r) and np.array_equal(y_o, y64)              # same sampled nodes, same pair labels
-    assert np.array_equal(p_o == 0, p_r == 0) and np.array_equal(p_o == 0, p64 == 0)   # same exact zeros
+    assert np.array_equal(p_o == 0, p64 == 0)                                 # same exact zeros as the float64 oracle
+    assert not ((p_r != 0) & (p_o == 0)).any()                                # the reference's float32 run can only lose tiny entries
     nz = p64 != 0
     rel = np.abs(p_o[nz] - p64[nz]) / np.abs(p64[nz])
     assert rel.max() <= 1e-3, rel.max()
@@ -116,12 +117,18 @@ def test_reference_main_dp_model_through_the_drop_in(dataset, perturb, fn):
     assert f"_{perturb}_" in ours[0] and "eps-5.0_seed-42" in ours[0]
 
 
-def test_reference_main_lsa2_baseline_through_the_drop_in(dataset):
+@pytest.mark.parametrize("mode", ["baseline", "baseline-feat"])
+def test_reference_main_lsa2_baselines_through_the_drop_in(dataset, mode):
     td, _, _ = dataset
-    extra = ["--mode", "vanilla-clean", "--sample-type", "unbalanced", "--attack-mode", "baseline"]
+    extra = ["--mode", "vanilla-clean", "--sample-type", "unbalanced", "--attack-mode", mode]
     (rel_r, d_r, auc_r, _), (rel_o, d_o, auc_o, _) = run_main(td, False, extra), run_main(td, True, extra)
     assert rel_o == rel_r
     p_r, p_o = np.asarray(d_r["result"]["pred"]), np.asarray(d_o["result"]["pred"])
-    assert np.array_equal(np.asarray(d_o["result"]["y"]), np.asarray(d_r["result"]["y"]))
+    y = np.asarray(d_o["result"]["y"])
+    assert np.array_equal(y, np.asarray(d_r["result"]["y"]))
     assert np.abs(p_o - p_r).max() <= 2e-5 * max(1.0, np.abs(p_r).max())
-    assert abs(auc_o - auc_r) <= 1e-3
+    assert abs(auc_o - O.auc_ap(y, p_o)[0]) <= 1e-9                 # the printed AUC is the AUC of the saved scores
+    if mode == "baseline-feat":
+        # raw features: well conditioned.  (The posterior variant on this random, saturated model yields correlations
+        # within 1e-6 of ±1, so its ranking — and AUC — is decided by float32 noise in either implementation.)
+        assert abs(auc_o - auc_r) <= 1e-3
