@@ -276,9 +276,25 @@ def main():
     T = wl.T
     out = torch.empty((T, T), dtype=torch.float32, device=dev)
     group = dist.group.WORLD if world > 1 else None
+    comm, exchange = None, "single GPU"
+    if world > 1:
+        # every rank must take the same branch: agree on whether all of them mapped their peers
+        ok = torch.ones(1, device=dev)
+        try:
+            comm = attack.make_node_comm(group, T, dev)
+        except Exception as e:                                   # no P2P / IPC on this box: NCCL all-gather of the dense rows
+            ok.zero_()
+            if rank == 0:
+                print(f"[bench] peer mapping failed ({e}); falling back to the NCCL all-gather", file=sys.stderr)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if ok.item() == 0:
+            comm = None
+        exchange = ("reduce kernel stores into every rank's matrix over NVLink (CUDA IPC peer memory, no collective)" if comm
+                    else "NCCL all_gather_into_tensor of the dense rows")
 
     def step():
-        return attack.influence_matrix(wl.adj_hat, wl.x, wl.w1, wl.b1, wl.w2, wl.test_nodes, wl.delta, out=out, group=group)
+        return attack.influence_matrix(wl.adj_hat, wl.x, wl.w1, wl.b1, wl.w2, wl.test_nodes, wl.delta, out=out, group=group,
+                                       comm=comm)
 
     def barrier():
         if world > 1:
@@ -347,7 +363,7 @@ def main():
         def host_step():
             return attack.influence_matrix_host(host["indptr"], host["indices"], host["values"], host["x"], host["w1"],
                                                 host["b1"], host["w2"], host["test_nodes"], wl.delta, device=dev,
-                                                stage=stage, group=group)
+                                                stage=stage, group=group, comm=comm)
         for _ in range(2):
             host_step()
         barrier()
@@ -439,7 +455,7 @@ def main():
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": bench_config(wl.describe(), world),
-            "l2_flush_between_steps": bool(flush), "options": list(args.opt),
+            "l2_flush_between_steps": bool(flush), "options": list(args.opt), "exchange": exchange,
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline, "roofline_frontier": roofline_frontier,
             "phases_ms_per_step": {k: round(v, 4) for k, v in per_step.items()},
@@ -451,6 +467,11 @@ def main():
             line.update(cpu_legs(wl, info, out, args))
         print(json.dumps(line), flush=True)
     if world > 1:
+        if comm is not None:
+            if comm.timed_out() and rank == 0:
+                print("[bench] a peer wait timed out during the run", file=sys.stderr)
+            dist.barrier()
+            comm.close()
         dist.barrier()
         dist.destroy_process_group()
 

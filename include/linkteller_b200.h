@@ -45,6 +45,7 @@ extern "C" {
 
 typedef void* lt_stream_t; /* cudaStream_t */
 typedef struct lt_plan lt_plan;
+typedef struct lt_comm lt_comm;
 
 const char* lt_last_error(void);
 int lt_version(void);
@@ -242,6 +243,30 @@ int64_t lt_launch_count(void); /* kernels launched by this library in this proce
 int lt_prof_enable(int on);
 int lt_prof_reset(void);
 int lt_prof_report(char* buf_host, int64_t cap);
+
+/* ---------------------------------------------------------------------------------------------
+ * Several GPUs of one node (the reference has no multi-device code to replace: grep finds no
+ * torch.distributed / NCCL / MPI call site).  One process per GPU.  lt_comm_create allocates this rank's symmetric buffer
+ * (`bytes` of payload: the full T x T float32 influence matrix) and returns its 64-byte CUDA IPC handle through
+ * lt_comm_get_handle; the caller exchanges the handles of all ranks (any host-side channel) and hands the world x 64 bytes,
+ * in rank order, to lt_comm_open, which maps every peer buffer into this process.  lt_attack_efficient_comm is
+ * lt_attack_efficient for rank `rank`: it perturbs test_nodes[lo:hi) and its reduce kernel stores the influence entries it
+ * produces into EVERY rank's matrix (st.global on the mapped peer pointers, carried by NVLink / NVSwitch), ordered by
+ * epoch flags with system-scope fences — there is no collective call and no dense all-gather.  On return (stream order)
+ * lt_comm_buffer(comm) holds all T rows.  Every rank must make the call for every attack, also with hi == lo.  Waits are
+ * bounded (≈ 2 s); lt_comm_timed_out reports (and clears) a wait that gave up.  Synchronising calls: create, open,
+ * timed_out, destroy.
+ * ------------------------------------------------------------------------------------------- */
+int lt_comm_create(int rank, int world, int64_t bytes, lt_comm** comm_host);
+int lt_comm_get_handle(const lt_comm* comm, void* handle64_host);
+int lt_comm_open(lt_comm* comm, const void* all_handles_host);
+void* lt_comm_buffer(const lt_comm* comm);
+int lt_comm_timed_out(lt_comm* comm, int* flag_host);
+int lt_comm_destroy(lt_comm* comm);
+int lt_attack_efficient_comm(const int32_t* indptr, const int32_t* indices, const float* values, int32_t n, const float* X,
+                             int64_t ldx, int32_t f, const float* W1, const float* b1, const float* W2, int32_t h, int32_t c,
+                             const int32_t* test_nodes, int32_t T, int32_t lo, int32_t hi, float delta, lt_comm* comm,
+                             int64_t* info_host /* nullable */, lt_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Process-wide tuning / debugging switches.  The reference has no counterpart (its only knobs are main.py's argparse

@@ -55,6 +55,13 @@ _SIGS = {
     "lt_pair_gather": [P, I64, I32, I32, P, P, I64, P, P],
     "lt_dp_edgerand_apply": [P, P, P, I32, P, P, I64, P, P, P, I64, P, P],
     "lt_dp_lapgraph_select": [P, P, P, I32, P, I64, P, P, P, I64, P, P],
+    "lt_comm_create": [INT, INT, I64, P],
+    "lt_comm_get_handle": [P, P],
+    "lt_comm_open": [P, P],
+    "lt_comm_buffer": [P],
+    "lt_comm_timed_out": [P, P],
+    "lt_comm_destroy": [P],
+    "lt_attack_efficient_comm": [P, P, P, I32, P, I64, I32, P, P, P, I32, I32, P, I32, I32, I32, F32, P, P, P],
     "lt_set_option": [C.c_char_p, INT],
     "lt_get_option": [C.c_char_p, P],
     "lt_launch_count": [],
@@ -64,7 +71,7 @@ _SIGS = {
     "lt_exclusive_scan_i32": [P, P, I64, P],
     "lt_radix_sort_pairs_u64": [P, P, I64, INT, INT, P],
 }
-_RESTYPE = {"lt_last_error": C.c_char_p, "lt_plan_rows": P, "lt_launch_count": I64}
+_RESTYPE = {"lt_last_error": C.c_char_p, "lt_plan_rows": P, "lt_launch_count": I64, "lt_comm_buffer": P}
 
 
 class LibraryMissing(RuntimeError):

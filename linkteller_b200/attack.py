@@ -34,12 +34,30 @@ def _world(group):
     return torch.distributed.get_world_size(group), torch.distributed.get_rank(group)
 
 
+def make_node_comm(group, T: int, device) -> ops.NodeComm:
+    """Symmetric influence matrices for the ranks of `group` (one node): CUDA IPC handles are exchanged with
+    all_gather_object.  Raises if the peers cannot be mapped (no P2P / IPC): callers then keep the NCCL all-gather."""
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+
+    def exchange(mine: bytes):
+        got = [None] * world
+        dist.all_gather_object(got, mine, group=group)
+        return got
+    return ops.NodeComm(rank, world, T, device, exchange)
+
+
 def influence_matrix(adj_hat: ops.DeviceCSR, x, w1, b1, w2, test_nodes: torch.Tensor, delta: float,
-                     group=None, out: Optional[torch.Tensor] = None, want_info: bool = False):
+                     group=None, out: Optional[torch.Tensor] = None, want_info: bool = False, comm=None):
     """[T,T] float32 influence matrix on the device; row i = perturb test_nodes[i], column j =
-    ‖Δlogits[test_nodes[j]]‖₂/δ.  With a process group (passed explicitly), rows are sharded and all-gathered."""
+    ‖Δlogits[test_nodes[j]]‖₂/δ.  With a process group (passed explicitly), rows are sharded: through `comm`
+    (make_node_comm) every rank's reduce kernel stores its entries straight into all ranks' matrices over NVLink and the
+    result is comm.matrix; without it the dense rows are all-gathered with NCCL into `out`."""
     T = test_nodes.numel()
     world, rank = _world(group)
+    if comm is not None:
+        lo, hi = slice_bounds(T, comm.world, comm.rank)
+        return ops.attack_efficient_comm(adj_hat, x, w1, b1, w2, test_nodes, delta, comm, lo, hi, want_info=want_info)
     if out is None:
         out = torch.empty((T, T), dtype=torch.float32, device=x.device)
     lo, hi = slice_bounds(T, world, rank)
@@ -103,6 +121,22 @@ class HostStage:
         d.copy_(p, non_blocking=True)
         return d
 
+    def to_device_sharded(self, key, arr, device, world, rank, group):
+        """Upload this rank's 1/world slice of `arr` and all-gather the slices (NCCL over NVLink) into the full array."""
+        import torch.distributed as dist
+        t = torch.from_numpy(np.ascontiguousarray(arr)) if isinstance(arr, np.ndarray) else arr.contiguous()
+        flat = t.reshape(-1)
+        chunk = -(-flat.numel() // world)
+        full = self._dev.get(key)
+        if full is None or full.numel() != chunk * world or full.dtype != t.dtype:
+            full = torch.empty(chunk * world, dtype=t.dtype, device=device)
+            self._dev[key] = full
+        lo, hi = rank * chunk, min((rank + 1) * chunk, flat.numel())
+        if hi > lo:
+            full[lo:hi].copy_(flat[lo:hi], non_blocking=True)        # pinned when `arr` came from adopt()
+        dist.all_gather_into_tensor(full, full[rank * chunk:(rank + 1) * chunk], group=group)
+        return full[:flat.numel()].view(t.shape)
+
     def pinned(self, key, shape, dtype):
         p = self._pinned.get(key)
         if p is None or tuple(p.shape) != tuple(shape) or p.dtype != dtype:
@@ -122,21 +156,32 @@ class HostStage:
 
 
 def influence_matrix_host(indptr, indices, values, x, w1, b1, w2, test_nodes, delta: float, device="cuda",
-                          stage: Optional[HostStage] = None, group=None):
+                          stage: Optional[HostStage] = None, group=None, comm=None):
     """Host buffers in (Â as CSR int32/int32/float32, X, weights, test nodes), influence matrix out
     in (pinned) host memory.  Every call copies all inputs host→device and the result device→host.
-    Returns (matrix [T,T] float32 CPU tensor, h2d_bytes, d2h_bytes)."""
+
+    One rank: everything goes over this GPU's PCIe link.  Several ranks (explicit `group`): every rank holds the same
+    host buffers (the reference's Worker is replicated per process), uploads only ITS 1/world slice of the three large
+    arrays (indices, values, X) and the slices are all-gathered over NVLink — the host link carries each byte once per
+    node instead of once per GPU; the small arrays are uploaded whole.  Only rank 0 reads the matrix back.
+    Returns (matrix [T,T] float32 CPU tensor — None on ranks > 0, h2d_bytes of the whole node, d2h_bytes)."""
     stage = stage or HostStage()
+    world, rank = _world(group)
     d = {}
     h2d = 0
     for key, arr in (("indptr", indptr), ("indices", indices), ("values", values), ("x", x), ("w1", w1), ("b1", b1),
                      ("w2", w2), ("test_nodes", test_nodes)):
-        d[key] = stage.to_device(key, arr, device)
-        h2d += d[key].numel() * d[key].element_size()
+        if world > 1 and key in ("indices", "values", "x"):
+            d[key] = stage.to_device_sharded(key, arr, device, world, rank, group)
+        else:
+            d[key] = stage.to_device(key, arr, device)
+        h2d += d[key].numel() * d[key].element_size() * (1 if key in ("indices", "values", "x") else world)
     n = d["indptr"].numel() - 1
     adj = ops.DeviceCSR(d["indptr"], d["indices"], d["values"], n)
-    out = influence_matrix(adj, d["x"], d["w1"], d["b1"], d["w2"], d["test_nodes"], delta, group=group)
-    host = stage.pinned("out", out.shape, out.dtype)
-    host.copy_(out, non_blocking=True)
+    out = influence_matrix(adj, d["x"], d["w1"], d["b1"], d["w2"], d["test_nodes"], delta, group=group, comm=comm)
+    host = None
+    if rank == 0:
+        host = stage.pinned("out", out.shape, out.dtype)
+        host.copy_(out, non_blocking=True)
     torch.cuda.current_stream().synchronize()
     return host, h2d, out.numel() * out.element_size()

@@ -165,6 +165,23 @@ bool hub_applicable(int32_t n_cols, int64_t ldb, int32_t d, const float* B);
 int hub_prepare(const int32_t* indptr, int32_t n, const float* B, int64_t ldb, int32_t d, HubPanel* out, Scratch& scratch,
                 cudaStream_t s);
 
+// ---- lt_comm (comm.cu): one symmetric buffer per rank, mapped into every rank of the node with CUDA IPC ----
+constexpr int LT_MAX_RANKS = 8;
+}  // namespace lt
+struct lt_comm {
+    int rank = 0, world = 1;
+    size_t bytes = 0;                      // payload bytes of every rank's buffer
+    void* peer[lt::LT_MAX_RANKS] = {};     // base of rank r's buffer in THIS process (peer[rank] = the local allocation)
+    uint32_t* flags[lt::LT_MAX_RANKS] = {};  // rank r's flag block: [2][LT_MAX_RANKS] epochs ("zeroed", "rows written") by writer rank
+    uint32_t epoch = 0;                    // attacks run so far (every rank calls in lock step)
+    int* timeout_flag = nullptr;           // device word set by a wait that gave up
+    bool opened = false;
+    unsigned char handle[64] = {};         // cudaIpcMemHandle_t of the local allocation
+};
+namespace lt {
+int comm_signal(lt_comm* c, int which, cudaStream_t s);   // which: 0 = "my matrix is zero-filled", 1 = "my rows are written"
+int comm_wait(lt_comm* c, int which, cudaStream_t s);
+
 // ---- primitives implemented in scan.cu / radix_sort.cu ----
 // out has n+1 entries: out[0] = 0, out[k] = sum(in[0..k)), out[n] = total.  in may alias out.
 int exclusive_scan_i32(const int32_t* in, int32_t* out, int64_t n, cudaStream_t s);

@@ -337,6 +337,28 @@ k_frontier_dq(const int32_t* __restrict__ s_j, const int32_t* __restrict__ s_rho
 constexpr int F2_BIG = 64;
 constexpr int F2_BIG_WARPS = 32;   // 1024-thread CTA per big group
 
+// Where F2 writes an influence entry.  One GPU: the caller's row block.  Several GPUs (lt_attack_efficient_comm): the
+// SAME entry goes into the full matrix of every rank — base[r] is rank r's matrix, mapped into this process by CUDA IPC,
+// so the stores to r != rank travel over NVLink / NVSwitch from inside the reduce kernel and no collective follows it.
+struct OutDst {
+    float* base[LT_MAX_RANKS];
+    int32_t n;          // destinations
+    int64_t row0;       // row of the matrix that slice row 0 maps to (0 when base[0] is the caller's row block)
+    int64_t ldo;
+    __device__ __forceinline__ void store(uint64_t key, float v) const {
+        const int64_t off = ((int64_t)(key >> 32) + row0) * ldo + (int64_t)(key & 0xffffffffu);
+#pragma unroll
+        for (int d = 0; d < LT_MAX_RANKS; ++d)
+            if (d < n) base[d][off] = v;
+    }
+};
+static inline OutDst single_dst(float* out, int64_t ldo) {
+    OutDst d;
+    for (int i = 0; i < LT_MAX_RANKS; ++i) d.base[i] = nullptr;
+    d.base[0] = out; d.n = 1; d.row0 = 0; d.ldo = ldo;
+    return d;
+}
+
 __device__ __forceinline__ float f2_column(const uint64_t* __restrict__ val, const float* __restrict__ dq, int32_t c /* row stride of dq */,
                                            int col, int32_t m0, int32_t m1) {
     float z0 = 0.f, z1 = 0.f, z2 = 0.f, z3 = 0.f;
@@ -361,7 +383,7 @@ template <int G>
 __global__ void __launch_bounds__(256)
 k_frontier_reduce(const uint64_t* __restrict__ key, const uint64_t* __restrict__ val,
                   const int32_t* __restrict__ grp_off, const int32_t* __restrict__ n_groups,
-                  const float* __restrict__ dq, int32_t lddq, int32_t c, float* __restrict__ out, int64_t ldo) {
+                  const float* __restrict__ dq, int32_t lddq, int32_t c, OutDst out) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t g = t / G;
     const int sub = (int)(t % G);
@@ -420,7 +442,7 @@ k_frontier_reduce(const uint64_t* __restrict__ key, const uint64_t* __restrict__
     }
 #pragma unroll
     for (int o = 1; o < G; o <<= 1) ss += __shfl_xor_sync(LT_FULL, ss, o);
-    if (valid && sub == 0) out[(int64_t)(k0 >> 32) * ldo + (int64_t)(k0 & 0xffffffffu)] = sqrtf(ss);
+    if (valid && sub == 0) out.store(k0, sqrtf(ss));
 }
 
 // thread per group: append the groups with more than F2_BIG records to big[]
@@ -436,8 +458,7 @@ __global__ void k_big_groups(const int32_t* __restrict__ grp_off, const int32_t*
 __global__ void __launch_bounds__(32 * F2_BIG_WARPS)
 k_frontier_reduce_big(const uint64_t* __restrict__ key, const uint64_t* __restrict__ val,
                       const int32_t* __restrict__ grp_off, const int32_t* __restrict__ big,
-                      const int32_t* __restrict__ n_big, const float* __restrict__ dq, int32_t lddq, int32_t c,
-                      float* __restrict__ out, int64_t ldo) {
+                      const int32_t* __restrict__ n_big, const float* __restrict__ dq, int32_t lddq, int32_t c, OutDst out) {
     __shared__ float part[F2_BIG_WARPS][32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int32_t b = blockIdx.x; b < *n_big; b += gridDim.x) {
@@ -461,8 +482,7 @@ k_frontier_reduce_big(const uint64_t* __restrict__ key, const uint64_t* __restri
         if (warp == 0) {
             ss = warp_sum(ss);
             if (lane == 0) {
-                const uint64_t k0 = key[m0];
-                out[(int64_t)(k0 >> 32) * ldo + (int64_t)(k0 & 0xffffffffu)] = sqrtf(ss);
+                out.store(key[m0], sqrtf(ss));
             }
         }
     }
@@ -1161,7 +1181,7 @@ static int frontier_dq_signs(const lt_plan* p, const uint32_t* sign_words, int32
 // out[j,i] = ‖Σ_k w_k·ΔQ[e_k,:]‖₂ for every group of sorted records (F2)
 static int frontier_reduce(const uint64_t* rec_key, const uint64_t* rec_val, const int32_t* grp_off, const int32_t* n_groups,
                            const int32_t* big, const int32_t* n_big, int64_t M, const float* dq, int32_t lddq, int32_t c,
-                           float* out, int64_t ldo, cudaStream_t s) {
+                           const OutDst& out, cudaStream_t s) {
     if (M == 0) return LT_OK;
     ProfScope prof2("frontier_reduce", s);
     // groups above F2_BIG records (a CTA each) write other output pairs than the small groups: they go first, on the
@@ -1183,11 +1203,11 @@ static int frontier_reduce(const uint64_t* rec_key, const uint64_t* rec_val, con
     StreamJoin join(s, side);
     if (M > F2_BIG) {
         k_frontier_reduce_big<<<(unsigned)num_sms() * 2, 32 * F2_BIG_WARPS, 0, side>>>(rec_key, rec_val, grp_off, big, n_big, dq, lddq,
-                                                                                       c, out, ldo);
+                                                                                       c, out);
         LT_LAUNCH_CHECK();
     }
 #define LT_F2(G_)                                                                                              \
-    k_frontier_reduce<G_><<<(unsigned)ceil_div(M * G_, 256), 256, 0, s>>>(rec_key, rec_val, grp_off, n_groups, dq, lddq, c, out, ldo)
+    k_frontier_reduce<G_><<<(unsigned)ceil_div(M * G_, 256), 256, 0, s>>>(rec_key, rec_val, grp_off, n_groups, dq, lddq, c, out)
     // lanes per group: a group is a couple of records, so half a warp with up to four columns per lane keeps more
     // groups in flight than a whole warp (C5, c = 47: 0.188 → 0.171 ms; 8 lanes 0.189, 4 lanes 0.209)
     if (c <= 1) LT_F2(1);
@@ -1203,16 +1223,18 @@ static int frontier_reduce(const uint64_t* rec_key, const uint64_t* rec_val, con
 
 int influence_rows(const lt_plan* p, const float* H_R, int64_t ldh, const float* P, int64_t ldp,
                    const int32_t* p_index, const float* W2, int32_t h, int32_t c, float delta, float* out,
-                   int64_t ldo, cudaStream_t s, const FixCtx* fix = nullptr, int32_t* n_fixed_host = nullptr) {
+                   int64_t ldo, cudaStream_t s, const FixCtx* fix = nullptr, int32_t* n_fixed_host = nullptr,
+                   const OutDst* dst = nullptr /* multi-GPU: every rank's matrix, already zero-filled */) {
     const int64_t E = p->E, M = p->M;
-    LT_CUDA(cudaMemset2DAsync(out, (size_t)ldo * 4, 0, (size_t)p->T * 4, (size_t)p->Ts, s));
+    if (!dst) LT_CUDA(cudaMemset2DAsync(out, (size_t)ldo * 4, 0, (size_t)p->T * 4, (size_t)p->Ts, s));
     if (E == 0 || M == 0) return LT_OK;
     Scratch scratch(s);
     float* dq;
     const int32_t lddq = frontier_lddq(E, h, c);
     LT_TRY(scratch.alloc(&dq, (size_t)E * lddq));
     LT_TRY(frontier_dq(p, p->s_rho, H_R, ldh, P, ldp, p_index, W2, h, c, delta, dq, s, fix, n_fixed_host));
-    return frontier_reduce(p->rec_key, p->rec_val, p->grp_off, p->n_groups, p->big, p->n_big, M, dq, lddq, c, out, ldo, s);
+    return frontier_reduce(p->rec_key, p->rec_val, p->grp_off, p->n_groups, p->big, p->n_big, M, dq, lddq, c,
+                           dst ? *dst : single_dst(out, ldo), s);
 }
 
 static void plan_info(const lt_plan* p, int32_t h, int32_t c, int64_t* info) {
@@ -1457,7 +1479,7 @@ static int gcn3_chunk(const int32_t* indptr, const int32_t* indices, const float
         LT_TRY(radix_sort_u64(key3, val3, M3, ranges, Ts > 1 ? 2 : 1, s));
         LT_TRY(group_records(key3, M3, grp3, ng3, big3, nbig3, scratch, s));
     }
-    LT_TRY(frontier_reduce(key3, val3, grp3, ng3, big3, nbig3, M3, dq2, c, c, out, ldo, s));
+    LT_TRY(frontier_reduce(key3, val3, grp3, ng3, big3, nbig3, M3, dq2, c, c, single_dst(out, ldo), s));
     if (info) {
         int32_t g = 0;
         LT_CUDA(cudaMemcpyAsync(&g, ng3, 4, cudaMemcpyDeviceToHost, s));
@@ -1682,29 +1704,46 @@ int attack_early(lt_plan* plan, void* vctx, cudaStream_t side) {
 }
 }  // namespace
 
-extern "C" int lt_attack_efficient(const int32_t* indptr, const int32_t* indices, const float* values, int32_t n,
-                                   const float* X, int64_t ldx, int32_t f, const float* W1, const float* b1,
-                                   const float* W2, int32_t h, int32_t c, const int32_t* test_nodes, int32_t T,
-                                   int32_t lo, int32_t hi, float delta, float* out, int64_t ldo, int64_t* info_host,
-                                   lt_stream_t stream) {
-    LT_CHECK_ARG(indptr && indices && values && test_nodes, "lt_attack_efficient: null pointer");
-    LT_CHECK_ARG(X && W1 && b1 && W2 && out, "lt_attack_efficient: null pointer");
-    LT_CHECK_ARG(f > 0 && h > 0 && c > 0 && ldx >= f && h % 4 == 0, "lt_attack_efficient: sizes (h % 4 == 0)");
-    LT_CHECK_ARG(n > 0 && T > 0 && lo >= 0 && hi >= lo && hi <= T && ldo >= T,
-                 "lt_attack_efficient: need 0 <= lo <= hi <= T <= ldo");
-    LT_CHECK_ARG(delta != 0.f, "lt_attack_efficient: delta must not be 0");
-    cudaStream_t s = (cudaStream_t)stream;
-    if (hi == lo) return LT_OK;
+static int attack_efficient_impl(const int32_t* indptr, const int32_t* indices, const float* values, int32_t n, const float* X,
+                                 int64_t ldx, int32_t f, const float* W1, const float* b1, const float* W2, int32_t h, int32_t c,
+                                 const int32_t* test_nodes, int32_t T, int32_t lo, int32_t hi, float delta, float* out, int64_t ldo,
+                                 lt_comm* comm, int64_t* info_host, cudaStream_t s) {
     lt_plan* plan = new lt_plan();
     plan->n = n; plan->T = T; plan->lo = lo; plan->hi = hi; plan->Ts = hi - lo;
-    int st;
+    int st = LT_OK;
     {
         Scratch scratch(s);
         AttackCtx a{indptr, indices, values, n, X, ldx, f, W1, b1, h, c, test_nodes, lo, s, &scratch};
-        st = scratch.alloc(&a.Pt, (size_t)plan->Ts * h);
+        st = scratch.alloc(&a.Pt, (size_t)(plan->Ts > 0 ? plan->Ts : 1) * h);
         struct EvGuard { cudaEvent_t* e; ~EvGuard() { if (*e) cudaEventDestroy(*e); } } hub_guard{&a.hub_ready};
+        cudaEvent_t zero_done = nullptr;
+        EvGuard zero_guard{&zero_done};
+        OutDst dst = single_dst(out, ldo);
+        if (st == LT_OK && comm) {
+            // every rank clears ITS matrix (next to the plan, on the side stream) and tells the others; the reduce kernel
+            // further down then stores this rank's entries into all of them (comm.cu)
+            ++comm->epoch;
+            for (int r = 0; r < comm->world; ++r) dst.base[r] = static_cast<float*>(comm->peer[r]);
+            dst.n = comm->world; dst.row0 = lo; dst.ldo = T;
+            cudaStream_t sd = overlap_enabled() ? side_stream() : nullptr;
+            cudaStream_t run = sd ? sd : s;
+            cudaEvent_t fork = nullptr;
+            if (run != s) {
+                if (cudaEventCreateWithFlags(&fork, cudaEventDisableTiming) != cudaSuccess || cudaEventRecord(fork, s) != cudaSuccess ||
+                    cudaStreamWaitEvent(run, fork, 0) != cudaSuccess) { set_error("lt_attack_efficient_comm: fork failed"); st = LT_ERR_CUDA; }
+                if (fork) cudaEventDestroy(fork);
+            }
+            if (st == LT_OK && cudaMemsetAsync(comm->peer[comm->rank], 0, (size_t)T * T * 4, run) != cudaSuccess) {
+                set_error("lt_attack_efficient_comm: cudaMemsetAsync failed"); st = LT_ERR_CUDA;
+            }
+            if (st == LT_OK) st = comm_signal(comm, 0, run);
+            if (st == LT_OK && run != s &&
+                (cudaEventCreateWithFlags(&zero_done, cudaEventDisableTiming) != cudaSuccess || cudaEventRecord(zero_done, run) != cudaSuccess)) {
+                set_error("lt_attack_efficient_comm: event failed"); st = LT_ERR_CUDA;
+            }
+        }
         // hub panel of X for the aggregate-first SpMM: built next to the plan head, on the side stream
-        if (st == LT_OK && f < h && hub_applicable(n, ldx, f, X) && T >= 1024) {
+        if (st == LT_OK && hi > lo && f < h && hub_applicable(n, ldx, f, X) && T >= 1024) {
             cudaStream_t sd = overlap_enabled() ? side_stream() : nullptr;
             cudaStream_t run = sd ? sd : s;
             st = hub_prepare(indptr, n, X, ldx, f, &a.hub, scratch, run);
@@ -1716,16 +1755,24 @@ extern "C" int lt_attack_efficient(const int32_t* indptr, const int32_t* indices
                 }
             }
         }
-        if (st == LT_OK)
-            st = plan_build(plan, indptr, indices, values, test_nodes, s, overlap_enabled() ? attack_early : nullptr, &a);
-        if (st == LT_OK && !overlap_enabled()) st = attack_early(plan, &a, s);
-        const FixCtx fix{indptr, indices, values, X, ldx, f, W1, b1, test_nodes + lo, plan->rows};
         int32_t n_fixed = 0;
-        if (st == LT_OK) {
+        const bool work = hi > lo;
+        if (st == LT_OK && work)
+            st = plan_build(plan, indptr, indices, values, test_nodes, s, overlap_enabled() ? attack_early : nullptr, &a);
+        if (st == LT_OK && work && !overlap_enabled()) st = attack_early(plan, &a, s);
+        const FixCtx fix{indptr, indices, values, X, ldx, f, W1, b1, test_nodes + lo, plan->rows};
+        // several GPUs: nobody's matrix may still be clearing when the reduce kernel starts storing into it
+        auto before_reduce = [&]() -> int {
+            if (!comm) return LT_OK;
+            if (zero_done && cudaStreamWaitEvent(s, zero_done, 0) != cudaSuccess) { set_error("lt_attack_efficient_comm: wait failed"); return LT_ERR_CUDA; }
+            ProfScope prof("comm_wait_zeroed", s);
+            return comm_wait(comm, 0, s);
+        };
+        if (st == LT_OK && work) {
             if (a.sign_path) {
                 const int32_t lddq = frontier_lddq(plan->E, h, c);
                 float* dq = nullptr;
-                if (cudaMemset2DAsync(out, (size_t)ldo * 4, 0, (size_t)T * 4, (size_t)plan->Ts, s) != cudaSuccess) {
+                if (!comm && cudaMemset2DAsync(out, (size_t)ldo * 4, 0, (size_t)T * 4, (size_t)plan->Ts, s) != cudaSuccess) {
                     set_error("lt_attack_efficient: cudaMemset2DAsync failed");
                     st = LT_ERR_CUDA;
                 }
@@ -1733,21 +1780,69 @@ extern "C" int lt_attack_efficient(const int32_t* indptr, const int32_t* indices
                     st = scratch.alloc(&dq, (size_t)plan->E * lddq);
                     if (st == LT_OK)
                         st = frontier_dq_signs(plan, a.signs, a.wpr, a.minabs, fix, a.Pt, h, nullptr, W2, h, c, delta, dq, &n_fixed, s);
+                    if (st == LT_OK) st = before_reduce();
                     if (st == LT_OK)
                         st = frontier_reduce(plan->rec_key, plan->rec_val, plan->grp_off, plan->n_groups, plan->big, plan->n_big,
-                                             plan->M, dq, lddq, c, out, ldo, s);
+                                             plan->M, dq, lddq, c, dst, s);
+                } else if (st == LT_OK) {
+                    st = before_reduce();
                 }
             } else {
-                st = influence_rows(plan, a.HR, h, a.Pt, h, nullptr, W2, h, c, delta, out, ldo, s, &fix, &n_fixed);
+                st = before_reduce();
+                if (st == LT_OK) st = influence_rows(plan, a.HR, h, a.Pt, h, nullptr, W2, h, c, delta, out, ldo, s, &fix, &n_fixed, comm ? &dst : nullptr);
             }
+        } else if (st == LT_OK) {
+            st = before_reduce();
+        }
+        if (st == LT_OK && comm) {
+            // this rank's entries are in every matrix; the local one is complete once every peer says the same
+            ProfScope prof("comm_exchange", s);
+            st = comm_signal(comm, 1, s);
+            if (st == LT_OK) st = comm_wait(comm, 1, s);
         }
         if (st == LT_OK && info_host) {
-            st = lt_plan_info(plan, h, c, info_host, stream);
+            if (work) st = lt_plan_info(plan, h, c, info_host, (lt_stream_t)s);
+            else for (int k = 0; k < 8; ++k) info_host[k] = 0;
             if (st == LT_OK) info_host[7] = n_fixed;      // incidences re-evaluated in float64 (a ReLU within reach of a switch)
         }
     }
-    lt_plan_destroy(plan, stream);
+    lt_plan_destroy(plan, (lt_stream_t)s);
     return st;
+}
+
+extern "C" int lt_attack_efficient(const int32_t* indptr, const int32_t* indices, const float* values, int32_t n,
+                                   const float* X, int64_t ldx, int32_t f, const float* W1, const float* b1,
+                                   const float* W2, int32_t h, int32_t c, const int32_t* test_nodes, int32_t T,
+                                   int32_t lo, int32_t hi, float delta, float* out, int64_t ldo, int64_t* info_host,
+                                   lt_stream_t stream) {
+    LT_CHECK_ARG(indptr && indices && values && test_nodes, "lt_attack_efficient: null pointer");
+    LT_CHECK_ARG(X && W1 && b1 && W2 && out, "lt_attack_efficient: null pointer");
+    LT_CHECK_ARG(f > 0 && h > 0 && c > 0 && ldx >= f && h % 4 == 0, "lt_attack_efficient: sizes (h % 4 == 0)");
+    LT_CHECK_ARG(n > 0 && T > 0 && lo >= 0 && hi >= lo && hi <= T && ldo >= T,
+                 "lt_attack_efficient: need 0 <= lo <= hi <= T <= ldo");
+    LT_CHECK_ARG(delta != 0.f, "lt_attack_efficient: delta must not be 0");
+    if (hi == lo) return LT_OK;
+    return attack_efficient_impl(indptr, indices, values, n, X, ldx, f, W1, b1, W2, h, c, test_nodes, T, lo, hi, delta, out, ldo,
+                                 nullptr, info_host, (cudaStream_t)stream);
+}
+
+// The same attack on one rank of a node-wide run: this rank perturbs test_nodes[lo:hi) and stores its influence entries
+// into the T x T matrix of EVERY rank of `comm` (peer memory over NVLink, comm.cu); on return (stream order) the local
+// matrix lt_comm_buffer(comm) holds all T rows.  Every rank of the communicator must make the call, also with hi == lo.
+extern "C" int lt_attack_efficient_comm(const int32_t* indptr, const int32_t* indices, const float* values, int32_t n,
+                                        const float* X, int64_t ldx, int32_t f, const float* W1, const float* b1,
+                                        const float* W2, int32_t h, int32_t c, const int32_t* test_nodes, int32_t T,
+                                        int32_t lo, int32_t hi, float delta, lt_comm* comm, int64_t* info_host,
+                                        lt_stream_t stream) {
+    LT_CHECK_ARG(indptr && indices && values && test_nodes && comm, "lt_attack_efficient_comm: null pointer");
+    LT_CHECK_ARG(X && W1 && b1 && W2, "lt_attack_efficient_comm: null pointer");
+    LT_CHECK_ARG(f > 0 && h > 0 && c > 0 && ldx >= f && h % 4 == 0, "lt_attack_efficient_comm: sizes (h % 4 == 0)");
+    LT_CHECK_ARG(n > 0 && T > 0 && lo >= 0 && hi >= lo && hi <= T, "lt_attack_efficient_comm: need 0 <= lo <= hi <= T");
+    LT_CHECK_ARG(delta != 0.f, "lt_attack_efficient_comm: delta must not be 0");
+    LT_CHECK_ARG(comm->opened && (size_t)T * T * 4 <= comm->bytes, "lt_attack_efficient_comm: communicator not opened or its buffer is smaller than T*T floats");
+    float* local = static_cast<float*>(comm->peer[comm->rank]);
+    return attack_efficient_impl(indptr, indices, values, n, X, ldx, f, W1, b1, W2, h, c, test_nodes, T, lo, hi, delta,
+                                 local + (int64_t)lo * T, T, comm, info_host, (cudaStream_t)stream);
 }
 
 // --n-layer 3: the same call for GCN3 (gcn/models.py:28-46)

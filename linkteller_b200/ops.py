@@ -331,6 +331,70 @@ def attack_efficient(adj: DeviceCSR, x, w1, b1, w2, test_nodes: torch.Tensor, de
     return out
 
 
+class NodeComm:
+    """The ranks of one node sharing their influence matrices (lt_comm): every rank owns a T x T float32 matrix in a
+    symmetric buffer that is mapped into all other ranks by CUDA IPC; lt_attack_efficient_comm stores each entry into all
+    of them from inside its reduce kernel.  `exchange(handle_bytes) -> list of every rank's handle bytes` is the host-side
+    channel (attack.make_node_comm uses torch.distributed.all_gather_object)."""
+
+    def __init__(self, rank: int, world: int, T: int, device, exchange):
+        lib = _lib.load()
+        self.rank, self.world, self.T = rank, world, T
+        self.device = torch.device(device)
+        self._h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(lib.lt_comm_create(rank, world, T * T * 4, C.byref(self._h)), "lt_comm_create")
+            hb = C.create_string_buffer(64)
+            _lib.check(lib.lt_comm_get_handle(self._h, hb), "lt_comm_get_handle")
+            handles = exchange(hb.raw)
+            if len(handles) != world or any(len(x) != 64 for x in handles):
+                raise RuntimeError("NodeComm: the handle exchange must return one 64-byte handle per rank")
+            _lib.check(lib.lt_comm_open(self._h, b"".join(handles)), "lt_comm_open")
+            ptr = lib.lt_comm_buffer(self._h)
+
+        class _Raw:                                         # torch wraps the library-owned buffer without copying
+            __cuda_array_interface__ = {"shape": (T, T), "typestr": "<f4", "data": (int(ptr), False), "version": 3,
+                                        "strides": None}
+        self._raw = _Raw()
+        self.matrix = torch.as_tensor(self._raw, device=self.device)
+
+    def timed_out(self) -> bool:
+        v = C.c_int()
+        _lib.check(_lib.load().lt_comm_timed_out(self._h, C.byref(v)), "lt_comm_timed_out")
+        return bool(v.value)
+
+    def close(self):
+        if self._h:
+            self.matrix = None
+            _lib.load().lt_comm_destroy(self._h)
+            self._h = C.c_void_p()
+
+
+def attack_efficient_comm(adj: DeviceCSR, x, w1, b1, w2, test_nodes: torch.Tensor, delta: float, comm: NodeComm,
+                          lo: int, hi: int, want_info: bool = False):
+    """lt_attack_efficient_comm: this rank perturbs test_nodes[lo:hi); returns comm.matrix, which holds all T rows once
+    the call's work on the current stream is done.  Every rank of the communicator must call."""
+    lib = _lib.load()
+    x, ldx = _rowmajor(x, "x")
+    w1 = _chk(w1, torch.float32, "w1", 2)
+    w2 = _chk(w2, torch.float32, "w2", 2)
+    _chk(b1, torch.float32, "b1", 1)
+    _chk(test_nodes, torch.int32, "test_nodes", 1)
+    _chk(adj.values, torch.float32, "adj.values", 1)
+    T = test_nodes.numel()
+    if T != comm.T:
+        raise ValueError(f"communicator was built for T = {comm.T}, attack has T = {T}")
+    n, f = x.shape
+    h, c = w2.shape
+    info = (C.c_int64 * 8)()
+    _lib.check(lib.lt_attack_efficient_comm(_p(adj.indptr), _p(adj.indices), _p(adj.values), n, _p(x), ldx, f, _p(w1), _p(b1),
+                                            _p(w2), h, c, _p(test_nodes), T, lo, hi, float(delta), comm._h,
+                                            info if want_info else None, _stream()), "lt_attack_efficient_comm")
+    if want_info:
+        return comm.matrix, dict(zip(INFO_KEYS, list(info)))
+    return comm.matrix
+
+
 INFO3_KEYS = ("chunks", "hop1_incidences", "hop2_records", "hop2_incidences", "hop3_records", "support_pairs",
               "reserved0", "reserved1")
 
