@@ -127,10 +127,11 @@ class HostStage:
         t = torch.from_numpy(np.ascontiguousarray(arr)) if isinstance(arr, np.ndarray) else arr.contiguous()
         flat = t.reshape(-1)
         chunk = -(-flat.numel() // world)
-        full = self._dev.get(key)
+        full = self._dev.get(key + "/flat")
         if full is None or full.numel() != chunk * world or full.dtype != t.dtype:
             full = torch.empty(chunk * world, dtype=t.dtype, device=device)
-            self._dev[key] = full
+            self._dev[key + "/flat"] = full
+            self._dev.pop(key, None)                                  # the whole-array twin adopt() made is not needed
         lo, hi = rank * chunk, min((rank + 1) * chunk, flat.numel())
         if hi > lo:
             full[lo:hi].copy_(flat[lo:hi], non_blocking=True)        # pinned when `arr` came from adopt()

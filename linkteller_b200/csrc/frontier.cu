@@ -691,7 +691,7 @@ k_exact_fix(const int32_t* __restrict__ slow_list, int32_t n_slow, const int32_t
             double* __restrict__ part, const float* __restrict__ P, int64_t ldp, const int32_t* __restrict__ p_index,
             const uint32_t* __restrict__ sign_words, int32_t wpr, const uint32_t* __restrict__ maxabs_bits,
             const float* __restrict__ H, int64_t ldh, const float* __restrict__ W2, int32_t h, int32_t cdim, float delta,
-            float inv_delta, float eps_scale, float* __restrict__ dq, int32_t lddq) {
+            float inv_delta, float eps_scale, float* __restrict__ corr /* [n_slow, cdim] */) {
     extern __shared__ float dsm[];                      // [h]
     for (int32_t q = blockIdx.x; q < n_slow; q += gridDim.x) {
         const int64_t e = slow_list[q];
@@ -752,12 +752,11 @@ k_exact_fix(const int32_t* __restrict__ slow_list, int32_t n_slow, const int32_t
         __syncthreads();
         for (int col = threadIdx.x; col < cdim; col += blockDim.x) {
             float acc = 0.f;
-            bool any = false;
             for (int k = 0; k < h; ++k) {
                 const float dk = dsm[k];
-                if (dk != 0.f) { acc = fmaf(dk, W2[(int64_t)k * cdim + col], acc); any = true; }
+                if (dk != 0.f) acc = fmaf(dk, W2[(int64_t)k * cdim + col], acc);
             }
-            if (any) dq[e * lddq + col] += acc;
+            corr[(int64_t)q * cdim + col] = acc;
         }
         __syncthreads();
     }
@@ -771,6 +770,22 @@ struct FixPinned {
     ~FixPinned() { if (h) cudaFreeHost(h); }
 };
 
+// dq[e,:] += corr[q,:] for the queued incidences (after F1 has written ΔQ)
+__global__ void k_fix_apply(const int32_t* __restrict__ slow_list, int32_t n_slow, const float* __restrict__ corr, int32_t c,
+                            float* __restrict__ dq, int32_t lddq) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)n_slow * c) return;
+    const int32_t q = (int32_t)(t / c), col = (int32_t)(t % c);
+    dq[(int64_t)slow_list[q] * lddq + col] += corr[t];
+}
+
+static cudaStream_t side_stream();
+static bool overlap_enabled();
+
+// The fix-up needs nothing F1 produces: once the host knows the queue length (read back while F1 is being queued) the
+// gather and the float64 evaluation run on the library's side stream NEXT TO F1 and leave their corrections in `corr`;
+// a last small kernel adds them to ΔQ after F1.  `n_groups_dev` (nullable) rides along in the same read-back so that F2
+// can size its grid by the number of output pairs instead of the number of records.
 template <typename LaunchF1>
 static int exact_fix_run(int mode, const lt_plan* p, const int32_t* s_row, const FixCtx& ctx, int32_t* slow_list,
                          int32_t* counters, const float* P, int64_t ldp, const int32_t* p_index,
@@ -782,34 +797,60 @@ static int exact_fix_run(int mode, const lt_plan* p, const int32_t* s_row, const
     cudaEvent_t ev;
     LT_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     struct EvGuard { cudaEvent_t e; ~EvGuard() { cudaEventDestroy(e); } } evg{ev};
+    pin.h[2] = -1;
     LT_CUDA(cudaMemcpyAsync(pin.h, counters, 8, cudaMemcpyDeviceToHost, s));
+    if (p->n_groups) LT_CUDA(cudaMemcpyAsync(pin.h + 2, p->n_groups, 4, cudaMemcpyDeviceToHost, s));
     LT_CUDA(cudaEventRecord(ev, s));
     LT_TRY(queue_f1());
     LT_CUDA(cudaEventSynchronize(ev));
     const int32_t n_slow = pin.h[0], total_seg = pin.h[1];
+    if (p->n_groups && pin.h[2] >= 0) const_cast<lt_plan*>(p)->n_groups_host = pin.h[2];
     if (n_fixed_host) *n_fixed_host = n_slow;
     if (n_slow == 0) return LT_OK;
-    ProfScope prof("frontier_fix", s);
-    Scratch scratch(s);
+    cudaStream_t sd = overlap_enabled() ? side_stream() : nullptr;
+    cudaStream_t run = sd ? sd : s;
+    if (run != s) LT_CUDA(cudaStreamWaitEvent(run, ev, 0));            // the queue is complete; F1 is not waited for
+    Scratch scratch(run);                                              // freed on `run`, after the apply kernel (see below)
     int32_t* seg_off;
     double* part;
+    float* corr;
     LT_TRY(scratch.alloc(&seg_off, (size_t)n_slow + 1));
     LT_TRY(scratch.alloc(&part, (size_t)total_seg * ctx.f));
-    k_fix_nseg<<<(unsigned)ceil_div(n_slow, 256), 256, 0, s>>>(slow_list, n_slow, s_row, ctx.rows, ctx.indptr, seg_off);
-    LT_LAUNCH_CHECK();
-    LT_TRY(exclusive_scan_i32(seg_off, seg_off, n_slow, s));
-    k_fix_gather<<<(unsigned)ceil_div((int64_t)total_seg * ((ctx.f + 127) / 128) * 32, 256), 256, 0, s>>>(slow_list, n_slow, seg_off,
-                                                                                                          s_row, ctx, part);
-    LT_LAUNCH_CHECK();
-    const unsigned grid = (unsigned)(n_slow < num_sms() * 4 ? n_slow : num_sms() * 4);
-    const size_t smem = (size_t)h * sizeof(float);
-    if (mode == 0)
-        k_exact_fix<0><<<grid, 256, smem, s>>>(slow_list, n_slow, seg_off, p->s_j, s_row, p->s_a, ctx, part, P, ldp, p_index,
-                                               sign_words, wpr, maxabs_bits, H, ldh, W2, h, c, delta, 1.0f / delta, eps_scale, dq, lddq);
-    else
-        k_exact_fix<1><<<grid, 256, smem, s>>>(slow_list, n_slow, seg_off, p->s_j, s_row, p->s_a, ctx, part, P, ldp, p_index,
-                                               sign_words, wpr, maxabs_bits, H, ldh, W2, h, c, delta, 1.0f / delta, eps_scale, dq, lddq);
-    LT_LAUNCH_CHECK();
+    LT_TRY(scratch.alloc(&corr, (size_t)n_slow * c));
+    {
+        ProfScope prof(run != s ? "frontier_fix_side" : "frontier_fix", run);
+        k_fix_nseg<<<(unsigned)ceil_div(n_slow, 256), 256, 0, run>>>(slow_list, n_slow, s_row, ctx.rows, ctx.indptr, seg_off);
+        LT_LAUNCH_CHECK();
+        LT_TRY(exclusive_scan_i32(seg_off, seg_off, n_slow, run));
+        k_fix_gather<<<(unsigned)ceil_div((int64_t)total_seg * ((ctx.f + 127) / 128) * 32, 256), 256, 0, run>>>(slow_list, n_slow, seg_off,
+                                                                                                                s_row, ctx, part);
+        LT_LAUNCH_CHECK();
+        const unsigned grid = (unsigned)(n_slow < num_sms() * 4 ? n_slow : num_sms() * 4);
+        const size_t smem = (size_t)h * sizeof(float);
+        if (mode == 0)
+            k_exact_fix<0><<<grid, 256, smem, run>>>(slow_list, n_slow, seg_off, p->s_j, s_row, p->s_a, ctx, part, P, ldp, p_index,
+                                                     sign_words, wpr, maxabs_bits, H, ldh, W2, h, c, delta, 1.0f / delta, eps_scale, corr);
+        else
+            k_exact_fix<1><<<grid, 256, smem, run>>>(slow_list, n_slow, seg_off, p->s_j, s_row, p->s_a, ctx, part, P, ldp, p_index,
+                                                     sign_words, wpr, maxabs_bits, H, ldh, W2, h, c, delta, 1.0f / delta, eps_scale, corr);
+        LT_LAUNCH_CHECK();
+    }
+    cudaEvent_t ev2;
+    LT_CUDA(cudaEventCreateWithFlags(&ev2, cudaEventDisableTiming));
+    EvGuard evg2{ev2};
+    if (run != s) {
+        LT_CUDA(cudaEventRecord(ev2, run));
+        LT_CUDA(cudaStreamWaitEvent(s, ev2, 0));
+    }
+    {
+        ProfScope prof("frontier_fix", s);
+        k_fix_apply<<<(unsigned)ceil_div((int64_t)n_slow * c, 256), 256, 0, s>>>(slow_list, n_slow, corr, c, dq, lddq);
+        LT_LAUNCH_CHECK();
+    }
+    if (run != s) {                                                    // the side stream frees corr only after the apply kernel
+        LT_CUDA(cudaEventRecord(ev2, s));
+        LT_CUDA(cudaStreamWaitEvent(run, ev2, 0));
+    }
     return LT_OK;
 }
 
@@ -1181,8 +1222,9 @@ static int frontier_dq_signs(const lt_plan* p, const uint32_t* sign_words, int32
 // out[j,i] = ‖Σ_k w_k·ΔQ[e_k,:]‖₂ for every group of sorted records (F2)
 static int frontier_reduce(const uint64_t* rec_key, const uint64_t* rec_val, const int32_t* grp_off, const int32_t* n_groups,
                            const int32_t* big, const int32_t* n_big, int64_t M, const float* dq, int32_t lddq, int32_t c,
-                           const OutDst& out, cudaStream_t s) {
+                           const OutDst& out, cudaStream_t s, int64_t n_groups_host = -1) {
     if (M == 0) return LT_OK;
+    const int64_t n_work = n_groups_host >= 0 ? n_groups_host : M;       // groups when the host knows their number, else ≤ M
     ProfScope prof2("frontier_reduce", s);
     // groups above F2_BIG records (a CTA each) write other output pairs than the small groups: they go first, on the
     // side stream, and run next to the small-group kernel.  The join is RAII: every exit path below (a failed launch
@@ -1207,7 +1249,7 @@ static int frontier_reduce(const uint64_t* rec_key, const uint64_t* rec_val, con
         LT_LAUNCH_CHECK();
     }
 #define LT_F2(G_)                                                                                              \
-    k_frontier_reduce<G_><<<(unsigned)ceil_div(M * G_, 256), 256, 0, s>>>(rec_key, rec_val, grp_off, n_groups, dq, lddq, c, out)
+    k_frontier_reduce<G_><<<(unsigned)ceil_div((n_work > 0 ? n_work : 1) * G_, 256), 256, 0, s>>>(rec_key, rec_val, grp_off, n_groups, dq, lddq, c, out)
     // lanes per group: a group is a couple of records, so half a warp with up to four columns per lane keeps more
     // groups in flight than a whole warp (C5, c = 47: 0.188 → 0.171 ms; 8 lanes 0.189, 4 lanes 0.209)
     if (c <= 1) LT_F2(1);
@@ -1646,6 +1688,7 @@ struct AttackCtx {
     int32_t wpr = 0;
     HubPanel hub;                       // hot rows of X kept in the L2 for the restricted SpMM (built on the side stream)
     cudaEvent_t hub_ready = nullptr;
+    cudaEvent_t pv_ready = nullptr;     // P_v = X[v]·W1 of the slice: started at entry on the side stream, needed by F1 only
 };
 
 int attack_early(lt_plan* plan, void* vctx, cudaStream_t side) {
@@ -1654,13 +1697,6 @@ int attack_early(lt_plan* plan, void* vctx, cudaStream_t side) {
     Scratch& scratch = *a.scratch;
     const int32_t R = plan->R, Ts = plan->Ts, n = a.n, f = a.f, h = a.h, c = a.c;
     (void)side;
-    {   // P_v = X[v]·W1 for the slice (gathered rows).  On the caller's stream: put on the side stream, its 64 big
-        // tensor-core CTAs wait for whole SMs to drain of SpMM CTAs and hold the rest of the plan up behind them
-        // (measured: SpMM 2.56 → 2.86 ms, side-stream plan 0.59 → 0.83 ms)
-        // float64 accumulation (algo 3): ΔR = Â[r,v]·P[v] carries these values straight into the result
-        ProfScope prof("gemm_pv", s);
-        LT_TRY(gemm_f32(a.X, a.ldx, a.test_nodes + a.lo, a.W1, h, 0, nullptr, 0, a.Pt, h, Ts, h, f, 3, s));
-    }
     const bool aggregate_first = (f < h) && (f % 4 == 0) && (a.ldx % 4 == 0) && ((uintptr_t)a.X % 16 == 0);
     // sign-mask path: H_R is never written — the GEMM keeps one bit per element and the row's smallest magnitude
     // (36 bytes per frontier row instead of 4h), F1 reads those, and the rows where a ReLU can switch are patched
@@ -1742,6 +1778,27 @@ static int attack_efficient_impl(const int32_t* indptr, const int32_t* indices, 
                 set_error("lt_attack_efficient_comm: event failed"); st = LT_ERR_CUDA;
             }
         }
+        // P_v = X[v]·W1 for the slice (gathered rows; float64 accumulation, algo 3: ΔR = Â[r,v]·P[v] carries these values
+        // straight into the result).  Nothing but the test nodes is needed: it runs next to the plan head.
+        EvGuard pv_guard{&a.pv_ready};
+        if (st == LT_OK && hi > lo) {
+            cudaStream_t sd = overlap_enabled() ? side_stream() : nullptr;
+            cudaStream_t run = sd ? sd : s;
+            if (run != s) {
+                cudaEvent_t fork = nullptr;
+                if (cudaEventCreateWithFlags(&fork, cudaEventDisableTiming) != cudaSuccess || cudaEventRecord(fork, s) != cudaSuccess ||
+                    cudaStreamWaitEvent(run, fork, 0) != cudaSuccess) { set_error("lt_attack_efficient: fork failed"); st = LT_ERR_CUDA; }
+                if (fork) cudaEventDestroy(fork);
+            }
+            if (st == LT_OK) {
+                ProfScope prof("gemm_pv", run);
+                st = gemm_f32(X, ldx, test_nodes + lo, W1, h, 0, nullptr, 0, a.Pt, h, plan->Ts, h, f, 3, run);
+            }
+            if (st == LT_OK && run != s &&
+                (cudaEventCreateWithFlags(&a.pv_ready, cudaEventDisableTiming) != cudaSuccess || cudaEventRecord(a.pv_ready, run) != cudaSuccess)) {
+                set_error("lt_attack_efficient: event failed"); st = LT_ERR_CUDA;
+            }
+        }
         // hub panel of X for the aggregate-first SpMM: built next to the plan head, on the side stream
         if (st == LT_OK && hi > lo && f < h && hub_applicable(n, ldx, f, X) && T >= 1024) {
             cudaStream_t sd = overlap_enabled() ? side_stream() : nullptr;
@@ -1760,6 +1817,9 @@ static int attack_efficient_impl(const int32_t* indptr, const int32_t* indices, 
         if (st == LT_OK && work)
             st = plan_build(plan, indptr, indices, values, test_nodes, s, overlap_enabled() ? attack_early : nullptr, &a);
         if (st == LT_OK && work && !overlap_enabled()) st = attack_early(plan, &a, s);
+        if (st == LT_OK && a.pv_ready && cudaStreamWaitEvent(s, a.pv_ready, 0) != cudaSuccess) {
+            set_error("lt_attack_efficient: wait failed"); st = LT_ERR_CUDA;
+        }
         const FixCtx fix{indptr, indices, values, X, ldx, f, W1, b1, test_nodes + lo, plan->rows};
         // several GPUs: nobody's matrix may still be clearing when the reduce kernel starts storing into it
         auto before_reduce = [&]() -> int {
@@ -1783,7 +1843,7 @@ static int attack_efficient_impl(const int32_t* indptr, const int32_t* indices, 
                     if (st == LT_OK) st = before_reduce();
                     if (st == LT_OK)
                         st = frontier_reduce(plan->rec_key, plan->rec_val, plan->grp_off, plan->n_groups, plan->big, plan->n_big,
-                                             plan->M, dq, lddq, c, dst, s);
+                                             plan->M, dq, lddq, c, dst, s, plan->n_groups_host);
                 } else if (st == LT_OK) {
                     st = before_reduce();
                 }
