@@ -245,6 +245,18 @@ int lt_prof_reset(void);
 int lt_prof_report(char* buf_host, int64_t cap);
 
 /* ---------------------------------------------------------------------------------------------
+ * f2 / f4  link_prediction_attack_efficient_balanced (attacker.py:250-284, --sample-type balanced-full) and the naive per-pair
+ *     attack (attacker.py:143-160 → get_gradient_eps, :87-97): one influence entry per LISTED (perturbed, observed) pair.
+ *     test_nodes: the T distinct perturbed nodes; pair k perturbs test_nodes[pair_j[k]] and observes node pair_obs[k] (any
+ *     node of the graph).  out[k] = ‖((f(X + δ·e_p x_pᵀ) − f(X))/δ)[o]‖₂.  Same precompute / F1 / float64 fix-up as
+ *     lt_attack_efficient; the reduce intersects N̂(p) ∩ N̂(o) per pair — no row block over all observers is formed.
+ * ------------------------------------------------------------------------------------------- */
+int lt_pair_influence(const int32_t* indptr, const int32_t* indices, const float* values, int32_t n, const float* X,
+                      int64_t ldx, int32_t f, const float* W1, const float* b1, const float* W2, int32_t h, int32_t c,
+                      const int32_t* test_nodes, int32_t T, const int32_t* pair_j, const int32_t* pair_obs, int64_t K,
+                      float delta, float* out, lt_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Several GPUs of one node (the reference has no multi-device code to replace: grep finds no
  * torch.distributed / NCCL / MPI call site).  One process per GPU.  lt_comm_create allocates this rank's symmetric buffer
  * (`bytes` of payload: the full T x T float32 influence matrix) and returns its 64-byte CUDA IPC handle through

@@ -273,12 +273,13 @@ class Attacker:
         else:
             # pairs among the T sampled nodes: their entries all live in the T x T influence matrix
             infl = self.influence_matrix()
-            pos = {int(nd): i for i, nd in enumerate(np.asarray(self.test_nodes))}
+            tn = np.asarray(self.test_nodes)
+            order = np.argsort(tn, kind="stable")                # node id → position in the sample, vectorised
 
             def listed(prs):
                 a = np.asarray(prs).reshape(-1, 2)
-                rows = torch.tensor([pos[int(v)] for v in a[:, 1]], dtype=torch.int32, device=self.device)
-                cols = torch.tensor([pos[int(u)] for u in a[:, 0]], dtype=torch.int32, device=self.device)
+                rows = torch.from_numpy(order[np.searchsorted(tn[order], a[:, 1])].astype(np.int32)).to(self.device)
+                cols = torch.from_numpy(order[np.searchsorted(tn[order], a[:, 0])].astype(np.int32)).to(self.device)
                 return ops.pair_gather(infl, rows, cols).cpu().numpy().astype(np.float64)
         ex = listed(self.exist_edges)
         torch.cuda.synchronize(self.device)

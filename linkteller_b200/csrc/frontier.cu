@@ -20,6 +20,7 @@
 #include "gemm_ws.cuh"
 
 #include <stdlib.h>
+#include <string.h>
 
 #include <mutex>
 
@@ -62,6 +63,7 @@ struct lt_plan {
     int32_t* seg_off = nullptr;   // [R+1] exclusive scan of the SpMM segment counts of the frontier rows
     int64_t total_seg = -1;       // its total (read back with the other sizes: the restricted SpMM needs no sync of its own)
     int32_t n_groups_host = -1;
+    bool listed_only = false;     // listed-pair mode (lt_pair_influence): incidences only, no observer lists / records
     void* owned[24];
     int n_owned = 0;
 };
@@ -69,68 +71,63 @@ struct lt_plan {
 namespace lt {
 
 // ------------------------------------------------------------------------------------ plan kernels
-__global__ void k_tmap(const int32_t* __restrict__ test_nodes, int32_t T, int32_t n, int32_t* __restrict__ tmap,
-                       int* __restrict__ err) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= T) return;
-    const int32_t v = test_nodes[i];
-    if (v < 0 || v >= n) { atomicOr(err, 1); return; }
-    if (atomicCAS(&tmap[v], -1, i) != -1) atomicOr(err, 2);  // duplicate test node
+// The frontier row set R = ∪_{v∈slice} N̂(v) is a bitmap over the nodes (n/32 words: 306 KB at n = 2.45 M, against the
+// 10 MB int flag / rank arrays of round 1) with an exclusive popcount prefix per word: the compact index of row r is
+// pref[r/32] + popc(bits[r/32] & below(r)), evaluated where it is needed instead of being stored for all n nodes.
+__device__ __forceinline__ int32_t frontier_rank(const uint32_t* __restrict__ bits, const int32_t* __restrict__ pref, int32_t r) {
+    const uint32_t b = bits[r >> 5], m = 1u << (r & 31);
+    return (b & m) ? pref[r >> 5] + __popc(b & (m - 1)) : -1;
 }
 
-// len[i] = nnz of row test_nodes[i] for all T; slice lens go to s_len
+// len[i] = nnz of row test_nodes[i] for all T; slice lens go to s_len.  A second bitmap catches duplicate test nodes.
 __global__ void k_test_lens(const int32_t* __restrict__ indptr, const int32_t* __restrict__ test_nodes, int32_t T,
                             int32_t n, int32_t lo, int32_t hi, int32_t* __restrict__ all_len, int32_t* __restrict__ s_len,
-                            int* __restrict__ err = nullptr) {
+                            int* __restrict__ err = nullptr, uint32_t* __restrict__ seen = nullptr) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= T) return;
     const int32_t v = test_nodes[i];
-    if ((v < 0 || v >= n) && err) atomicOr(err, 1);                           // reported with the first host sync
-    const int32_t len = (v >= 0 && v < n) ? indptr[v + 1] - indptr[v] : 0;
+    const bool ok = v >= 0 && v < n;
+    if (!ok && err) atomicOr(err, 1);                                         // reported with the first host sync
+    if (ok && seen && (atomicOr(&seen[v >> 5], 1u << (v & 31)) & (1u << (v & 31)))) atomicOr(err, 2);   // duplicate
+    const int32_t len = ok ? indptr[v + 1] - indptr[v] : 0;
     all_len[i] = len;
-    if (i >= lo && i < hi) s_len[i - lo] = len;
+    if (s_len && i >= lo && i < hi) s_len[i - lo] = len;
 }
 
-// one warp per slice row: flag[r] = 1 for every r in row v
+// one warp per slice row: set the bit of every r in row v
 __global__ void k_mark_rows(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
                             const int32_t* __restrict__ test_nodes, int32_t n, int32_t lo, int32_t Ts,
-                            int32_t* __restrict__ flag) {
+                            uint32_t* __restrict__ bits) {
     const int lane = threadIdx.x & 31;
     const int64_t j = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (j >= Ts) return;
     const int32_t v = test_nodes[lo + j];
     if (v < 0 || v >= n) return;
-    for (int32_t k = indptr[v] + lane; k < indptr[v + 1]; k += 32) flag[indices[k]] = 1;
-}
-
-// pos = exclusive scan of flag.  rmap[r] = compact index or -1; rows[compact] = r; nseg[compact] = SpMM segments of row r
-__global__ void k_compact_rows(const int32_t* __restrict__ flag, const int32_t* __restrict__ pos, int32_t n,
-                               const int32_t* __restrict__ indptr, int32_t* __restrict__ rmap,
-                               int32_t* __restrict__ rows, int32_t* __restrict__ nseg) {
-    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= n) return;
-    if (flag[r]) {
-        const int32_t p = pos[r];
-        rmap[r] = p;
-        rows[p] = (int32_t)r;
-        const int32_t len = indptr[r + 1] - indptr[r];
-        nseg[p] = len <= SPMM_SEG ? 1 : (len + SPMM_SEG - 1) / SPMM_SEG;
-    } else {
-        rmap[r] = -1;
+    for (int32_t k = indptr[v] + lane; k < indptr[v + 1]; k += 32) {
+        const int32_t r = indices[k];
+        const uint32_t m = 1u << (r & 31);
+        if (!(bits[r >> 5] & m)) atomicOr(&bits[r >> 5], m);                  // hubs are hit by many rows: test first
     }
 }
 
-// Σ over the marked rows of their SpMM segment counts and of their lengths (grid-stride, one atomic pair per CTA):
-// known before the first host sync, the restricted SpMM can be launched as soon as the rows are compacted.
+// thread per word: its popcount; Σ over the marked rows of their SpMM segment counts and of their lengths (one atomic
+// pair per CTA) — known before the first host sync, so the restricted SpMM can be launched right after the compaction
 __global__ void __launch_bounds__(256)
-k_seg_total(const int32_t* __restrict__ flag, const int32_t* __restrict__ indptr, int32_t n, unsigned long long* __restrict__ tot) {
+k_word_counts(const uint32_t* __restrict__ bits, int32_t n_words, const int32_t* __restrict__ indptr, int32_t* __restrict__ cnt,
+              unsigned long long* __restrict__ tot) {
+    const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long seg = 0, nnz = 0;
-    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x)
-        if (flag[r]) {
+    if (w < n_words) {
+        uint32_t b = bits[w];
+        cnt[w] = __popc(b);
+        while (b) {
+            const int32_t r = (int32_t)(w * 32) + __ffs(b) - 1;
+            b &= b - 1;
             const int32_t len = indptr[r + 1] - indptr[r];
             seg += len <= SPMM_SEG ? 1 : (len + SPMM_SEG - 1) / SPMM_SEG;
             nnz += len;
         }
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { seg += __shfl_xor_sync(LT_FULL, seg, o); nnz += __shfl_xor_sync(LT_FULL, nnz, o); }
     __shared__ unsigned long long sh[2][8];
@@ -138,9 +135,25 @@ k_seg_total(const int32_t* __restrict__ flag, const int32_t* __restrict__ indptr
     if (lane == 0) { sh[0][warp] = seg; sh[1][warp] = nnz; }
     __syncthreads();
     if (threadIdx.x == 0) {
-        for (int w = 1; w < 8; ++w) { seg += sh[0][w]; nnz += sh[1][w]; }
-        atomicAdd(&tot[0], seg);
-        atomicAdd(&tot[1], nnz);
+        for (int k = 1; k < 8; ++k) { seg += sh[0][k]; nnz += sh[1][k]; }
+        if (seg | nnz) { atomicAdd(&tot[0], seg); atomicAdd(&tot[1], nnz); }
+    }
+}
+
+// thread per word: rows[pref + k] = node id of its k-th set bit; nseg = SpMM segments of that row
+__global__ void k_compact_rows(const uint32_t* __restrict__ bits, const int32_t* __restrict__ pref, int32_t n_words,
+                               const int32_t* __restrict__ indptr, int32_t* __restrict__ rows, int32_t* __restrict__ nseg) {
+    const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n_words) return;
+    uint32_t b = bits[w];
+    int32_t p = pref[w];
+    while (b) {
+        const int32_t r = (int32_t)(w * 32) + __ffs(b) - 1;
+        b &= b - 1;
+        rows[p] = r;
+        const int32_t len = indptr[r + 1] - indptr[r];
+        nseg[p] = len <= SPMM_SEG ? 1 : (len + SPMM_SEG - 1) / SPMM_SEG;
+        ++p;
     }
 }
 
@@ -150,7 +163,7 @@ k_seg_total(const int32_t* __restrict__ flag, const int32_t* __restrict__ indptr
 // serialising thousands of binary searches in one warp.
 __global__ void k_fill_S(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
                          const float* __restrict__ values, const int32_t* __restrict__ test_nodes, int32_t lo,
-                         int32_t Ts, int64_t E, const int32_t* __restrict__ rmap,
+                         int32_t Ts, int64_t E, const uint32_t* __restrict__ bits, const int32_t* __restrict__ pref,
                          const int32_t* __restrict__ s_indptr, int32_t* __restrict__ s_j,
                          int32_t* __restrict__ s_rho, float* __restrict__ s_a, int* __restrict__ err) {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -164,7 +177,7 @@ __global__ void k_fill_S(const int32_t* __restrict__ indptr, const int32_t* __re
     if (p < re && indices[p] == v) a = values[p];
     else { a = 0.f; atomicOr(err, 4); }
     s_j[e] = j;
-    s_rho[e] = rmap[r];
+    s_rho[e] = frontier_rank(bits, pref, r);
     s_a[e] = a;
 }
 
@@ -174,13 +187,13 @@ __global__ void k_fill_S(const int32_t* __restrict__ indptr, const int32_t* __re
 template <int MODE>
 __global__ void k_observers(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
                             const float* __restrict__ values, const int32_t* __restrict__ test_nodes, int32_t T,
-                            const int32_t* __restrict__ all_off, const int32_t* __restrict__ rmap,
+                            const int32_t* __restrict__ all_off, const uint32_t* __restrict__ bits, const int32_t* __restrict__ pref,
                             int32_t* __restrict__ cnt_or_cursor, int32_t* __restrict__ b_i, float* __restrict__ b_w) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= all_off[T]) return;
     const int32_t i = (int32_t)upper_bound(all_off, 0, (int64_t)T + 1, (int32_t)t) - 1;
     const int32_t k = indptr[test_nodes[i]] + ((int32_t)t - all_off[i]);
-    const int32_t rho = rmap ? rmap[indices[k]] : indices[k];   // no map: observer lists over all n nodes
+    const int32_t rho = bits ? frontier_rank(bits, pref, indices[k]) : indices[k];   // no bitmap: observer lists over all n nodes
     if (rho < 0) return;
     if (MODE == 0) {
         atomicAdd(&cnt_or_cursor[rho], 1);
@@ -486,6 +499,63 @@ k_frontier_reduce_big(const uint64_t* __restrict__ key, const uint64_t* __restri
             }
         }
     }
+}
+
+// Listed pairs (link_prediction_attack_efficient_balanced / the naive attack: one entry per listed (perturbed, observed)
+// pair, attacker.py:250-284, 143-160).  One warp per pair: N̂(p) ∩ N̂(o) by a merge of the two sorted CSR rows (binary
+// search of the shorter row in the longer when they differ by more than 8x), Σ_r Â[o,r]·ΔQ_p[r,:] in ascending r, 2-norm.
+// ΔQ_p[r] is row s_indptr[j] + (position of r in row p) of dq.  Lanes ↔ columns (c ≤ 256).
+__global__ void __launch_bounds__(256)
+k_pair_reduce(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices, const float* __restrict__ values,
+              const int32_t* __restrict__ v_nodes /* node id of slice row j */, const int32_t* __restrict__ s_indptr,
+              const int32_t* __restrict__ pair_j, const int32_t* __restrict__ pair_obs, int64_t K,
+              const float* __restrict__ dq, int32_t lddq, int32_t c, float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t k = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (k >= K) return;
+    const int32_t j = pair_j[k], o = pair_obs[k];
+    const int32_t p = v_nodes[j];
+    const int32_t pa = indptr[p], pe = indptr[p + 1], oa = indptr[o], oe = indptr[o + 1];
+    const int64_t e0 = s_indptr[j];
+    float z[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) z[q] = 0.f;
+    auto hit = [&](int32_t a /* position in row p */, int32_t b /* position in row o */) {
+        const float w = values[b];
+        const float* row = dq + (e0 + (a - pa)) * lddq;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int col = lane + 32 * q;
+            if (col < c) z[q] = fmaf(w, row[col], z[q]);
+        }
+    };
+    const int32_t lp = pe - pa, lo_ = oe - oa;
+    if (lp > 8 * lo_) {                                   // few entries in row o: look each up in row p
+        for (int32_t b = oa; b < oe; ++b) {
+            const int32_t r = indices[b];
+            const int64_t a = lower_bound(indices, (int64_t)pa, (int64_t)pe, r);
+            if (a < pe && indices[a] == r) hit((int32_t)a, b);
+        }
+    } else if (lo_ > 8 * lp) {
+        for (int32_t a = pa; a < pe; ++a) {
+            const int32_t r = indices[a];
+            const int64_t b = lower_bound(indices, (int64_t)oa, (int64_t)oe, r);
+            if (b < oe && indices[b] == r) hit(a, (int32_t)b);
+        }
+    } else {
+        int32_t a = pa, b = oa;
+        while (a < pe && b < oe) {
+            const int32_t ra = indices[a], rb = indices[b];
+            if (ra == rb) { hit(a, b); ++a; ++b; }
+            else if (ra < rb) ++a;
+            else ++b;
+        }
+    }
+    float ss = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) ss = fmaf(z[q], z[q], ss);
+    ss = warp_sum(ss);
+    if (lane == 0) out[k] = sqrtf(ss);
 }
 
 // A operand of the tensor-core F1: row e of ΔR, computed from one H row, one P row and a_e
@@ -919,49 +989,53 @@ static int plan_build(lt_plan* p, const int32_t* indptr, const int32_t* indices,
     const int32_t n = p->n, T = p->T, lo = p->lo, Ts = p->Ts;
     Scratch scratch(s);
     struct ScopeBox { ProfScope* p; ~ScopeBox() { delete p; } void end() { delete p; p = nullptr; } } prof_a{new ProfScope("plan", s)};
-    int32_t *tmap, *rmap, *flag, *all_len;
-    int* err;
-    LT_TRY(scratch.alloc(&tmap, (size_t)n));
-    LT_TRY(scratch.alloc(&rmap, (size_t)n));
-    LT_TRY(scratch.alloc(&flag, (size_t)n + 1));
+    const int32_t n_words = (n + 31) / 32;
+    // one zero-filled block: [frontier bitmap | test-node bitmap | Σ segments, Σ nnz (2 x u64) | err]
+    uint32_t* zero_blk;
+    int32_t *all_len, *cnt, *pref;
+    const size_t zero_words = (size_t)2 * n_words + 6;
+    LT_TRY(scratch.alloc(&zero_blk, zero_words));
     LT_TRY(scratch.alloc(&all_len, (size_t)T + 1));
-    LT_TRY(scratch.alloc(&err, 1));
+    LT_TRY(scratch.alloc(&cnt, (size_t)n_words + 1));
+    LT_TRY(scratch.alloc(&pref, (size_t)n_words + 1));
+    uint32_t* bits = zero_blk;
+    uint32_t* seen = zero_blk + n_words;
+    unsigned long long* seg_tot = reinterpret_cast<unsigned long long*>(zero_blk + 2 * (size_t)n_words);   // word offset 2·n_words: 8-byte aligned
+    int* err = reinterpret_cast<int*>(zero_blk + zero_words - 1);
     LT_TRY(plan_alloc(p, &p->s_indptr, (size_t)Ts + 1, s));
-    LT_CUDA(cudaMemsetAsync(flag, 0, ((size_t)n + 1) * 4, s));
-    LT_CUDA(cudaMemsetAsync(err, 0, sizeof(int), s));
-    int herr = 0;   // read back with the sizes of the second sync; until then invalid test nodes are skipped, not dereferenced
-    k_test_lens<<<(unsigned)ceil_div(T, 256), 256, 0, s>>>(indptr, test_nodes, T, n, lo, p->hi, all_len, p->s_indptr, err);
+    LT_CUDA(cudaMemsetAsync(zero_blk, 0, zero_words * 4, s));
+    k_test_lens<<<(unsigned)ceil_div(T, 256), 256, 0, s>>>(indptr, test_nodes, T, n, lo, p->hi, all_len, p->s_indptr, err, seen);
+    LT_LAUNCH_CHECK();
+    k_mark_rows<<<(unsigned)ceil_div((int64_t)Ts * 32, 256), 256, 0, s>>>(indptr, indices, test_nodes, n, lo, Ts, bits);
     LT_LAUNCH_CHECK();
     LT_TRY(exclusive_scan_i32(all_len, all_len, T, s));
     LT_TRY(exclusive_scan_i32(p->s_indptr, p->s_indptr, Ts, s));
-    k_mark_rows<<<(unsigned)ceil_div((int64_t)Ts * 32, 256), 256, 0, s>>>(indptr, indices, test_nodes, n, lo, Ts, flag);
+    k_word_counts<<<(unsigned)ceil_div(n_words, 256), 256, 0, s>>>(bits, n_words, indptr, cnt, seg_tot);
     LT_LAUNCH_CHECK();
-    int32_t* pos;
-    LT_TRY(scratch.alloc(&pos, (size_t)n + 1));
-    LT_TRY(exclusive_scan_i32(flag, pos, n, s));
-    unsigned long long* seg_tot;
-    unsigned long long h_seg_tot[2] = {0, 0};
-    LT_TRY(scratch.alloc(&seg_tot, 2));
-    LT_CUDA(cudaMemsetAsync(seg_tot, 0, 16, s));
-    k_seg_total<<<(unsigned)num_sms() * 8, 256, 0, s>>>(flag, indptr, n, seg_tot);
-    LT_LAUNCH_CHECK();
-    int32_t h3[3];
-    LT_CUDA(cudaMemcpyAsync(h_seg_tot, seg_tot, 16, cudaMemcpyDeviceToHost, s));
-    LT_CUDA(cudaMemcpyAsync(&h3[0], p->s_indptr + Ts, 4, cudaMemcpyDeviceToHost, s));
-    LT_CUDA(cudaMemcpyAsync(&h3[1], pos + n, 4, cudaMemcpyDeviceToHost, s));
-    LT_CUDA(cudaMemcpyAsync(&h3[2], all_len + T, 4, cudaMemcpyDeviceToHost, s));
-    LT_CUDA(cudaMemcpyAsync(&herr, err, sizeof(int), cudaMemcpyDeviceToHost, s));
+    LT_TRY(exclusive_scan_i32(cnt, pref, n_words, s));
+    static thread_local FixPinned pin;              // pinned landing zone of the size read-back
+    if (!pin.h) LT_CUDA(cudaHostAlloc((void**)&pin.h, 64, cudaHostAllocDefault));
+    int32_t* hs = pin.h;                            // [0..3] Σ seg, Σ nnz (2 x u64) | [4] E | [5] R | [6] Σ all lens | [7] err
+    LT_CUDA(cudaMemcpyAsync(hs, seg_tot, 16, cudaMemcpyDeviceToHost, s));
+    LT_CUDA(cudaMemcpyAsync(hs + 4, p->s_indptr + Ts, 4, cudaMemcpyDeviceToHost, s));
+    LT_CUDA(cudaMemcpyAsync(hs + 5, pref + n_words, 4, cudaMemcpyDeviceToHost, s));
+    LT_CUDA(cudaMemcpyAsync(hs + 6, all_len + T, 4, cudaMemcpyDeviceToHost, s));
+    LT_CUDA(cudaMemcpyAsync(hs + 7, err, 4, cudaMemcpyDeviceToHost, s));
     LT_CUDA(cudaStreamSynchronize(s));
+    int herr = hs[7];
     if (herr & 1) { set_error("lt_plan_create: test node outside [0,%d)", n); return LT_ERR_DATA; }
-    p->E = h3[0];
-    p->R = h3[1];
-    const int64_t nb_cap = h3[2];
+    if (herr & 2) { set_error("lt_plan_create: duplicate test node"); return LT_ERR_DATA; }
+    unsigned long long h_seg_tot[2];
+    memcpy(h_seg_tot, hs, 16);
+    p->E = hs[4];
+    p->R = hs[5];
+    const int64_t nb_cap = hs[6];
     const int32_t R = p->R;
     const int64_t E = p->E;
 
     LT_TRY(plan_alloc(p, &p->rows, (size_t)R, s));
     LT_TRY(plan_alloc(p, &p->seg_off, (size_t)R + 1, s));
-    k_compact_rows<<<(unsigned)ceil_div(n, 256), 256, 0, s>>>(flag, pos, n, indptr, rmap, p->rows, p->seg_off);
+    k_compact_rows<<<(unsigned)ceil_div(n_words, 256), 256, 0, s>>>(bits, pref, n_words, indptr, p->rows, p->seg_off);
     LT_LAUNCH_CHECK();
     LT_TRY(exclusive_scan_i32(p->seg_off, p->seg_off, R, s));
     p->total_seg = (int64_t)h_seg_tot[0];
@@ -987,17 +1061,23 @@ static int plan_build(lt_plan* p, const int32_t* indptr, const int32_t* indices,
     s = s2;                                     // everything below runs on the side stream (or still on the caller's)
     Scratch scratch2(s);
     ProfScope prof_b(s2 != join.main ? "plan_side" : "plan", s);
-    // duplicate check of the test nodes (reported with the second sync; the range check came with the first)
-    LT_CUDA(cudaMemsetAsync(tmap, 0xff, (size_t)n * 4, s));
-    k_tmap<<<(unsigned)ceil_div(T, 256), 256, 0, s>>>(test_nodes, T, n, tmap, err);
-    LT_LAUNCH_CHECK();
     LT_TRY(plan_alloc(p, &p->s_j, (size_t)E, s));
     LT_TRY(plan_alloc(p, &p->s_rho, (size_t)E, s));
     LT_TRY(plan_alloc(p, &p->s_a, (size_t)E, s));
     if (E) {
-        k_fill_S<<<(unsigned)ceil_div(E, 256), 256, 0, s>>>(indptr, indices, values, test_nodes, lo, Ts, E, rmap,
+        k_fill_S<<<(unsigned)ceil_div(E, 256), 256, 0, s>>>(indptr, indices, values, test_nodes, lo, Ts, E, bits, pref,
                                                             p->s_indptr, p->s_j, p->s_rho, p->s_a, err);
         LT_LAUNCH_CHECK();
+    }
+
+    if (p->listed_only) {                       // the listed-pair reduce intersects rows itself: no observers, no records
+        LT_CUDA(cudaMemcpyAsync(&herr, err, sizeof(int), cudaMemcpyDeviceToHost, s));
+        LT_CUDA(cudaStreamSynchronize(s));
+        if (herr & 4) {
+            set_error("lt_pair_influence: Â[r,v] missing for a stored Â[v,r] — the adjacency pattern is not symmetric");
+            return LT_ERR_DATA;
+        }
+        return LT_OK;
     }
 
     // observers
@@ -1008,11 +1088,11 @@ static int plan_build(lt_plan* p, const int32_t* indptr, const int32_t* indices,
     LT_TRY(plan_alloc(p, &p->b_w, (size_t)nb_cap, s));
     LT_CUDA(cudaMemsetAsync(p->b_indptr, 0, ((size_t)R + 1) * 4, s));
     const unsigned blT = (unsigned)ceil_div(nb_cap > 0 ? nb_cap : 1, 256);
-    k_observers<0><<<blT, 256, 0, s>>>(indptr, indices, values, test_nodes, T, all_len, rmap, p->b_indptr, nullptr, nullptr);
+    k_observers<0><<<blT, 256, 0, s>>>(indptr, indices, values, test_nodes, T, all_len, bits, pref, p->b_indptr, nullptr, nullptr);
     LT_LAUNCH_CHECK();
     LT_TRY(exclusive_scan_i32(p->b_indptr, p->b_indptr, R, s));
     LT_CUDA(cudaMemcpyAsync(cursor, p->b_indptr, ((size_t)R + 1) * 4, cudaMemcpyDeviceToDevice, s));
-    k_observers<1><<<blT, 256, 0, s>>>(indptr, indices, values, test_nodes, T, all_len, rmap, cursor, p->b_i, p->b_w);
+    k_observers<1><<<blT, 256, 0, s>>>(indptr, indices, values, test_nodes, T, all_len, bits, pref, cursor, p->b_i, p->b_w);
     LT_LAUNCH_CHECK();
 
     // records
@@ -1582,11 +1662,11 @@ int attack_efficient3(const int32_t* indptr, const int32_t* indices, const float
     LT_TRY(scratch.alloc(&b_w, (size_t)nb_cap));
     LT_CUDA(cudaMemsetAsync(b_indptr, 0, ((size_t)n + 1) * 4, s));
     const unsigned blT = (unsigned)ceil_div(nb_cap > 0 ? nb_cap : 1, 256);
-    k_observers<0><<<blT, 256, 0, s>>>(indptr, indices, values, test_nodes, T, all_len, nullptr, b_indptr, nullptr, nullptr);
+    k_observers<0><<<blT, 256, 0, s>>>(indptr, indices, values, test_nodes, T, all_len, nullptr, nullptr, b_indptr, nullptr, nullptr);
     LT_LAUNCH_CHECK();
     LT_TRY(exclusive_scan_i32(b_indptr, b_indptr, n, s));
     LT_CUDA(cudaMemcpyAsync(cursor, b_indptr, ((size_t)n + 1) * 4, cudaMemcpyDeviceToDevice, s));
-    k_observers<1><<<blT, 256, 0, s>>>(indptr, indices, values, test_nodes, T, all_len, nullptr, cursor, b_i, b_w);
+    k_observers<1><<<blT, 256, 0, s>>>(indptr, indices, values, test_nodes, T, all_len, nullptr, nullptr, cursor, b_i, b_w);
     LT_LAUNCH_CHECK();
 
     // ---- chunks of perturbed nodes: stage-2 records per chunk bounded by the memory budget
@@ -1740,12 +1820,26 @@ int attack_early(lt_plan* plan, void* vctx, cudaStream_t side) {
 }
 }  // namespace
 
+struct ListedPairs { const int32_t* pair_j; const int32_t* pair_obs; int64_t K; float* out; };
+
+static int pair_reduce(const lt_plan* p, const int32_t* indptr, const int32_t* indices, const float* values,
+                       const int32_t* v_nodes, const ListedPairs& lp, const float* dq, int32_t lddq, int32_t c, cudaStream_t s) {
+    if (lp.K == 0) return LT_OK;
+    if (c > 256) { set_error("lt_pair_influence: c = %d > 256 classes is not supported", c); return LT_ERR_ARG; }
+    ProfScope prof("pair_reduce", s);
+    k_pair_reduce<<<(unsigned)ceil_div(lp.K * 32, 256), 256, 0, s>>>(indptr, indices, values, v_nodes, p->s_indptr, lp.pair_j,
+                                                                     lp.pair_obs, lp.K, dq, lddq, c, lp.out);
+    LT_LAUNCH_CHECK();
+    return LT_OK;
+}
+
 static int attack_efficient_impl(const int32_t* indptr, const int32_t* indices, const float* values, int32_t n, const float* X,
                                  int64_t ldx, int32_t f, const float* W1, const float* b1, const float* W2, int32_t h, int32_t c,
                                  const int32_t* test_nodes, int32_t T, int32_t lo, int32_t hi, float delta, float* out, int64_t ldo,
-                                 lt_comm* comm, int64_t* info_host, cudaStream_t s) {
+                                 lt_comm* comm, int64_t* info_host, cudaStream_t s, const ListedPairs* listed = nullptr) {
     lt_plan* plan = new lt_plan();
     plan->n = n; plan->T = T; plan->lo = lo; plan->hi = hi; plan->Ts = hi - lo;
+    plan->listed_only = listed != nullptr;
     int st = LT_OK;
     {
         Scratch scratch(s);
@@ -1832,20 +1926,29 @@ static int attack_efficient_impl(const int32_t* indptr, const int32_t* indices, 
             if (a.sign_path) {
                 const int32_t lddq = frontier_lddq(plan->E, h, c);
                 float* dq = nullptr;
-                if (!comm && cudaMemset2DAsync(out, (size_t)ldo * 4, 0, (size_t)T * 4, (size_t)plan->Ts, s) != cudaSuccess) {
+                if (!comm && !listed && cudaMemset2DAsync(out, (size_t)ldo * 4, 0, (size_t)T * 4, (size_t)plan->Ts, s) != cudaSuccess) {
                     set_error("lt_attack_efficient: cudaMemset2DAsync failed");
                     st = LT_ERR_CUDA;
                 }
-                if (st == LT_OK && plan->E > 0 && plan->M > 0) {
+                if (st == LT_OK && plan->E > 0 && (plan->M > 0 || listed)) {
                     st = scratch.alloc(&dq, (size_t)plan->E * lddq);
                     if (st == LT_OK)
                         st = frontier_dq_signs(plan, a.signs, a.wpr, a.minabs, fix, a.Pt, h, nullptr, W2, h, c, delta, dq, &n_fixed, s);
                     if (st == LT_OK) st = before_reduce();
-                    if (st == LT_OK)
+                    if (st == LT_OK && !listed)
                         st = frontier_reduce(plan->rec_key, plan->rec_val, plan->grp_off, plan->n_groups, plan->big, plan->n_big,
                                              plan->M, dq, lddq, c, dst, s, plan->n_groups_host);
+                    if (st == LT_OK && listed) st = pair_reduce(plan, indptr, indices, values, test_nodes + lo, *listed, dq, lddq, c, s);
                 } else if (st == LT_OK) {
                     st = before_reduce();
+                }
+            } else if (listed) {                                    // value path: ΔQ from the stored H rows, then the pair reduce
+                const int32_t lddq = frontier_lddq(plan->E, h, c);
+                float* dq = nullptr;
+                if (plan->E > 0) {
+                    st = scratch.alloc(&dq, (size_t)plan->E * lddq);
+                    if (st == LT_OK) st = frontier_dq(plan, plan->s_rho, a.HR, h, a.Pt, h, nullptr, W2, h, c, delta, dq, s, &fix, &n_fixed);
+                    if (st == LT_OK) st = pair_reduce(plan, indptr, indices, values, test_nodes + lo, *listed, dq, lddq, c, s);
                 }
             } else {
                 st = before_reduce();
@@ -1861,7 +1964,7 @@ static int attack_efficient_impl(const int32_t* indptr, const int32_t* indices, 
             if (st == LT_OK) st = comm_wait(comm, 1, s);
         }
         if (st == LT_OK && info_host) {
-            if (work) st = lt_plan_info(plan, h, c, info_host, (lt_stream_t)s);
+            if (work && !listed) st = lt_plan_info(plan, h, c, info_host, (lt_stream_t)s);
             else for (int k = 0; k < 8; ++k) info_host[k] = 0;
             if (st == LT_OK) info_host[7] = n_fixed;      // incidences re-evaluated in float64 (a ReLU within reach of a switch)
         }
@@ -1884,6 +1987,24 @@ extern "C" int lt_attack_efficient(const int32_t* indptr, const int32_t* indices
     if (hi == lo) return LT_OK;
     return attack_efficient_impl(indptr, indices, values, n, X, ldx, f, W1, b1, W2, h, c, test_nodes, T, lo, hi, delta, out, ldo,
                                  nullptr, info_host, (cudaStream_t)stream);
+}
+
+// Listed pairs: out[k] = ‖((f(X + δ·e_p x_pᵀ) − f(X))/δ)[o_k]‖₂ for p = test_nodes[pair_j[k]], o_k = pair_obs[k] (any node) — what
+// link_prediction_attack_efficient_balanced (attacker.py:250-284) and the naive attack (attacker.py:143-160, 87-97) read one
+// entry at a time.  test_nodes: the T distinct perturbed nodes.  Same restricted precompute, F1 and float64 fix-up as
+// lt_attack_efficient; the reduce intersects N̂(p) and N̂(o) per pair, so no T x n row block is ever formed.
+extern "C" int lt_pair_influence(const int32_t* indptr, const int32_t* indices, const float* values, int32_t n, const float* X,
+                                 int64_t ldx, int32_t f, const float* W1, const float* b1, const float* W2, int32_t h, int32_t c,
+                                 const int32_t* test_nodes, int32_t T, const int32_t* pair_j, const int32_t* pair_obs, int64_t K,
+                                 float delta, float* out, lt_stream_t stream) {
+    LT_CHECK_ARG(indptr && indices && values && test_nodes && X && W1 && b1 && W2, "lt_pair_influence: null pointer");
+    LT_CHECK_ARG(K == 0 || (pair_j && pair_obs && out), "lt_pair_influence: null pair arrays");
+    LT_CHECK_ARG(f > 0 && h > 0 && c > 0 && ldx >= f && h % 4 == 0 && n > 0 && T > 0 && K >= 0 && delta != 0.f,
+                 "lt_pair_influence: sizes (h % 4 == 0)");
+    if (K == 0) return LT_OK;
+    const ListedPairs lp{pair_j, pair_obs, K, out};
+    return attack_efficient_impl(indptr, indices, values, n, X, ldx, f, W1, b1, W2, h, c, test_nodes, T, 0, T, delta, nullptr, T,
+                                 nullptr, nullptr, (cudaStream_t)stream, &lp);
 }
 
 // The same attack on one rank of a node-wide run: this rank perturbs test_nodes[lo:hi) and stores its influence entries

@@ -642,9 +642,12 @@ def pair_influence(adj: DeviceCSR, x, w1, b1, w2, perturbed: torch.Tensor, obser
                    block_bytes: int = 512 << 20, b2=None, w3=None) -> torch.Tensor:
     """‖((f(X + δ·e_p x_pᵀ) − f(X))/δ)[o]‖₂ for LISTED (perturbed p, observed o) node pairs — what
     link_prediction_attack_efficient_balanced (attacker.py:250-284) and the naive attack
-    (attacker.py:143-160) read one entry at a time.  Every node is a candidate observer, so influence
-    rows are produced in blocks of perturbed nodes (lt_attack_efficient over [lo,hi) of 0..n-1, at most
-    block_bytes of rows at a time) and the listed entries are gathered from each block.  float32 [K]."""
+    (attacker.py:143-160) read one entry at a time.  float32 [K].
+
+    Two-layer model: lt_pair_influence — incidences and ΔQ for the distinct perturbed nodes only, then one warp per
+    listed pair intersects N̂(p) ∩ N̂(o); nothing of size n x n (or rows x n) is formed, so balanced-full on a
+    Flickr-sized graph (every node perturbed, 900 K listed pairs) is a fraction of a second.
+    Three-layer model (b2, w3 given): influence rows in blocks of perturbed nodes (lt_attack_efficient3) and a gather."""
     lib = _lib.load()
     _chk(perturbed, torch.int32, "perturbed", 1)
     _chk(observed, torch.int32, "observed", 1)
@@ -658,6 +661,21 @@ def pair_influence(adj: DeviceCSR, x, w1, b1, w2, perturbed: torch.Tensor, obser
     if int(torch.minimum(perturbed.min(), observed.min())) < 0 or int(torch.maximum(perturbed.max(), observed.max())) >= n:
         raise IndexError("pair node outside the graph")
     w1, b1, w2 = _pad_first_hidden(w1, b1, w2)
+    if w3 is None:
+        x, ldx = _rowmajor(x, "x")
+        w1 = _chk(w1, torch.float32, "w1", 2)
+        w2 = _chk(w2, torch.float32, "w2", 2)
+        _chk(b1, torch.float32, "b1", 1)
+        _chk(adj.values, torch.float32, "adj.values", 1)
+        uniq, inv = torch.unique(perturbed, return_inverse=True)          # the distinct perturbed nodes, ascending
+        tn = uniq.to(torch.int32).contiguous()
+        pj = inv.to(torch.int32).contiguous()
+        f = x.shape[1]
+        h, c = w2.shape
+        _lib.check(lib.lt_pair_influence(_p(adj.indptr), _p(adj.indices), _p(adj.values), n, _p(x), ldx, f, _p(w1), _p(b1), _p(w2),
+                                         h, c, _p(tn), tn.numel(), _p(pj), _p(observed), K, float(delta), _p(out), _stream()),
+                   "lt_pair_influence")
+        return out[:K]
     all_nodes = torch.arange(n, dtype=torch.int32, device=x.device)
     need = torch.zeros(n, dtype=torch.bool, device=x.device)
     need[perturbed.long()] = True
@@ -668,10 +686,7 @@ def pair_influence(adj: DeviceCSR, x, w1, b1, w2, perturbed: torch.Tensor, obser
         hi = min(n, lo + rows_per_block)
         if not need[lo:hi].any():
             continue
-        if w3 is None:
-            attack_efficient(adj, x, w1, b1, w2, all_nodes, delta, lo=lo, hi=hi, out=buf[: hi - lo])
-        else:                                        # three-layer model: b2 and W3 given
-            attack_efficient3(adj, x, w1, b1, w2, b2, w3, all_nodes, delta, lo=lo, hi=hi, out=buf[: hi - lo])
+        attack_efficient3(adj, x, w1, b1, w2, b2, w3, all_nodes, delta, lo=lo, hi=hi, out=buf[: hi - lo])
         _lib.check(lib.lt_pair_gather(_p(buf), buf.stride(0), lo, hi - lo, _p(perturbed), _p(observed), K, _p(out),
                                       _stream()), "lt_pair_gather")
     return out[:K]
