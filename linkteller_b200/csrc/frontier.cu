@@ -94,20 +94,26 @@ __global__ void k_test_lens(const int32_t* __restrict__ indptr, const int32_t* _
     if (s_len && i >= lo && i < hi) s_len[i - lo] = len;
 }
 
-// one warp per slice row: set the bit of every r in row v
+// one thread per incidence e = (j, k-th entry of row v_j): set the bit of r.  (A warp per row left the kernel waiting
+// for the few test nodes with thousands of neighbours: 58 µs against 8.)
 __global__ void k_mark_rows(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
                             const int32_t* __restrict__ test_nodes, int32_t n, int32_t lo, int32_t Ts,
-                            uint32_t* __restrict__ bits) {
-    const int lane = threadIdx.x & 31;
-    const int64_t j = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (j >= Ts) return;
-    const int32_t v = test_nodes[lo + j];
-    if (v < 0 || v >= n) return;
-    for (int32_t k = indptr[v] + lane; k < indptr[v + 1]; k += 32) {
-        const int32_t r = indices[k];
+                            const int32_t* __restrict__ s_indptr, uint32_t* __restrict__ bits) {
+    const int64_t E = s_indptr[Ts];                       // not known on the host yet: fixed grid, strided
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < E; e += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t j = (int32_t)upper_bound(s_indptr, 0, (int64_t)Ts + 1, (int32_t)e) - 1;
+        const int32_t v = test_nodes[lo + j];             // valid: an invalid test node has length 0 and owns no incidence
+        const int32_t r = indices[indptr[v] + ((int32_t)e - s_indptr[j])];
         const uint32_t m = 1u << (r & 31);
-        if (!(bits[r >> 5] & m)) atomicOr(&bits[r >> 5], m);                  // hubs are hit by many rows: test first
+        if (!(bits[r >> 5] & m)) atomicOr(&bits[r >> 5], m);  // hubs are hit by many rows: test first
     }
+}
+
+static int mark_rows(const int32_t* indptr, const int32_t* indices, const int32_t* test_nodes, int32_t n, int32_t lo, int32_t Ts,
+                     const int32_t* s_indptr, uint32_t* bits, cudaStream_t s) {
+    k_mark_rows<<<(unsigned)num_sms() * 16, 256, 0, s>>>(indptr, indices, test_nodes, n, lo, Ts, s_indptr, bits);
+    LT_LAUNCH_CHECK();
+    return LT_OK;
 }
 
 // thread per word: its popcount; Σ over the marked rows of their SpMM segment counts and of their lengths (one atomic
@@ -703,7 +709,7 @@ __global__ void k_fix_nseg(const int32_t* __restrict__ slow_list, int32_t n_slow
 // warp per gather segment g: part[g, i] = Σ_{t in segment} (double)Â[r,t]·(double)X[col_t, i], entries in CSR order.
 // The (column, value) pairs of a segment are read 32 at a time and broadcast by shuffle; eight rows of X are in flight
 // per lane before their FMAs — walked one dependent load at a time, a 512-entry segment took 0.5 ms (r2c).
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256)      // launched with 128 threads at small f: 128 x 88 registers fit beside F1's persistent CTA
 k_fix_gather(const int32_t* __restrict__ slow_list, int32_t n_slow, const int32_t* __restrict__ seg_off,
              const int32_t* __restrict__ s_row, FixCtx c, double* __restrict__ part) {
     const int lane = threadIdx.x & 31;
@@ -755,7 +761,7 @@ k_fix_gather(const int32_t* __restrict__ slow_list, int32_t n_slow, const int32_
 // MODE 0: sign-mask form (what MaskProd fed F1), MODE 1: value form (DeltaRProd on the stored H row).
 // One CTA per queued incidence (grid-stride); shared: d[h] corrections.
 template <int MODE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256)      // launched with 128 threads at small f (resident next to F1's one-CTA-per-SM GEMM)
 k_exact_fix(const int32_t* __restrict__ slow_list, int32_t n_slow, const int32_t* __restrict__ seg_off,
             const int32_t* __restrict__ s_j, const int32_t* __restrict__ s_row, const float* __restrict__ s_a, FixCtx c,
             double* __restrict__ part, const float* __restrict__ P, int64_t ldp, const int32_t* __restrict__ p_index,
@@ -820,11 +826,21 @@ k_exact_fix(const int32_t* __restrict__ slow_list, int32_t n_slow, const int32_t
             dsm[k] = d;
         }
         __syncthreads();
+        // the handful of units with a correction, in ascending k (one thread lists them: h ≤ a few hundred)
+        int32_t* nzk = reinterpret_cast<int32_t*>(dsm + h);
+        if (threadIdx.x == 0) {
+            int32_t cnt = 0;
+            for (int k = 0; k < h; ++k)
+                if (dsm[k] != 0.f) nzk[1 + cnt++] = k;
+            nzk[0] = cnt;
+        }
+        __syncthreads();
+        const int32_t cnt = nzk[0];
         for (int col = threadIdx.x; col < cdim; col += blockDim.x) {
             float acc = 0.f;
-            for (int k = 0; k < h; ++k) {
-                const float dk = dsm[k];
-                if (dk != 0.f) acc = fmaf(dk, W2[(int64_t)k * cdim + col], acc);
+            for (int t = 0; t < cnt; ++t) {
+                const int k = nzk[1 + t];
+                acc = fmaf(dsm[k], W2[(int64_t)k * cdim + col], acc);
             }
             corr[(int64_t)q * cdim + col] = acc;
         }
@@ -892,16 +908,19 @@ static int exact_fix_run(int mode, const lt_plan* p, const int32_t* s_row, const
         k_fix_nseg<<<(unsigned)ceil_div(n_slow, 256), 256, 0, run>>>(slow_list, n_slow, s_row, ctx.rows, ctx.indptr, seg_off);
         LT_LAUNCH_CHECK();
         LT_TRY(exclusive_scan_i32(seg_off, seg_off, n_slow, run));
-        k_fix_gather<<<(unsigned)ceil_div((int64_t)total_seg * ((ctx.f + 127) / 128) * 32, 256), 256, 0, run>>>(slow_list, n_slow, seg_off,
-                                                                                                                s_row, ctx, part);
+        // small f: the fix-up is cheap and should run NEXT TO F1 (CTAs of 128 threads fit in the registers F1 leaves free);
+        // large f (twitch-shaped, f = 3170): it is the longer of the two, full-size CTAs finish it sooner
+        const int fix_threads = ctx.f <= 256 ? 128 : 256;
+        k_fix_gather<<<(unsigned)ceil_div((int64_t)total_seg * ((ctx.f + 127) / 128) * 32, fix_threads), fix_threads, 0, run>>>(
+            slow_list, n_slow, seg_off, s_row, ctx, part);
         LT_LAUNCH_CHECK();
-        const unsigned grid = (unsigned)(n_slow < num_sms() * 4 ? n_slow : num_sms() * 4);
-        const size_t smem = (size_t)h * sizeof(float);
+        const unsigned grid = (unsigned)(n_slow < num_sms() * 8 ? n_slow : num_sms() * 8);
+        const size_t smem = ((size_t)2 * h + 1) * sizeof(float);
         if (mode == 0)
-            k_exact_fix<0><<<grid, 256, smem, run>>>(slow_list, n_slow, seg_off, p->s_j, s_row, p->s_a, ctx, part, P, ldp, p_index,
+            k_exact_fix<0><<<grid, fix_threads, smem, run>>>(slow_list, n_slow, seg_off, p->s_j, s_row, p->s_a, ctx, part, P, ldp, p_index,
                                                      sign_words, wpr, maxabs_bits, H, ldh, W2, h, c, delta, 1.0f / delta, eps_scale, corr);
         else
-            k_exact_fix<1><<<grid, 256, smem, run>>>(slow_list, n_slow, seg_off, p->s_j, s_row, p->s_a, ctx, part, P, ldp, p_index,
+            k_exact_fix<1><<<grid, fix_threads, smem, run>>>(slow_list, n_slow, seg_off, p->s_j, s_row, p->s_a, ctx, part, P, ldp, p_index,
                                                      sign_words, wpr, maxabs_bits, H, ldh, W2, h, c, delta, 1.0f / delta, eps_scale, corr);
         LT_LAUNCH_CHECK();
     }
@@ -1006,10 +1025,9 @@ static int plan_build(lt_plan* p, const int32_t* indptr, const int32_t* indices,
     LT_CUDA(cudaMemsetAsync(zero_blk, 0, zero_words * 4, s));
     k_test_lens<<<(unsigned)ceil_div(T, 256), 256, 0, s>>>(indptr, test_nodes, T, n, lo, p->hi, all_len, p->s_indptr, err, seen);
     LT_LAUNCH_CHECK();
-    k_mark_rows<<<(unsigned)ceil_div((int64_t)Ts * 32, 256), 256, 0, s>>>(indptr, indices, test_nodes, n, lo, Ts, bits);
-    LT_LAUNCH_CHECK();
-    LT_TRY(exclusive_scan_i32(all_len, all_len, T, s));
     LT_TRY(exclusive_scan_i32(p->s_indptr, p->s_indptr, Ts, s));
+    LT_TRY(mark_rows(indptr, indices, test_nodes, n, lo, Ts, p->s_indptr, bits, s));
+    LT_TRY(exclusive_scan_i32(all_len, all_len, T, s));
     k_word_counts<<<(unsigned)ceil_div(n_words, 256), 256, 0, s>>>(bits, n_words, indptr, cnt, seg_tot);
     LT_LAUNCH_CHECK();
     LT_TRY(exclusive_scan_i32(cnt, pref, n_words, s));
