@@ -114,7 +114,7 @@ class ClockSampler:
 # ncu --set full captures committed under profiles/ (never measured inside a bench run: a run under ncu
 # is not a bench value).  Keyed by (workload, n_gpus, kernel family).
 NCU_TRAFFIC = {
-    ("large", 1, "spmm_ax"): (13.754050e9 + 0.160299e9, "profiles/r1k_ncu_top_summary.txt"),
+    ("large", 1, "spmm_ax"): (13.748901e9 + 0.162670e9, "profiles/r2q_ncu_large_summary.txt"),
 }
 
 
