@@ -36,7 +36,7 @@ __global__ void k_spmm_segcount(const int32_t* __restrict__ indptr, const int32_
 }
 
 
-// seg_meta[g] = {first entry, (segment index within its row << 9) | entries, output position il, segments of the row}: a warp
+// seg_meta[g] = {first entry, one past the last entry, output position il, segments of the row}: a warp of the product
 // reads its work item in ONE load instead of a 19-step binary search over seg_off followed by rows[] and indptr[]
 // (four dependent round trips before the first gather on a kernel that is bound by latency x bytes in flight).
 __global__ void k_spmm_segmeta(const int32_t* __restrict__ indptr, const int32_t* __restrict__ rows, const int32_t* __restrict__ sel,
@@ -48,10 +48,7 @@ __global__ void k_spmm_segmeta(const int32_t* __restrict__ indptr, const int32_t
     const int32_t beg = indptr[r], end = indptr[r + 1];
     const int32_t first = seg_off[i], nseg = seg_off[i + 1] - first;
     for (int32_t k = 0; k < nseg; ++k)
-    {
-        const int32_t s0 = beg + k * SPMM_SEG, cnt = min(end, s0 + SPMM_SEG) - s0;          // cnt ≤ 256 < 2^9, k < 2^23 (nnz < 2^31)
-        seg_meta[first + k] = make_int4(s0, (int32_t)(((uint32_t)k << 9) | (uint32_t)cnt), il, nseg);
-    }
+        seg_meta[first + k] = make_int4(beg + k * SPMM_SEG, min(end, beg + (k + 1) * SPMM_SEG), il, nseg);
 }
 
 // NV = float4 slices per lane (d ≤ 128·NV).  seg_off: exclusive scan of nseg (n_rows+1 entries).
@@ -80,16 +77,14 @@ __global__ void __launch_bounds__(SPMM_THREADS, MINB)
 k_spmm_vec(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices, const float* __restrict__ values,
            const int32_t* __restrict__ rows, const int32_t* __restrict__ sel, int32_t n_rows, const int32_t* __restrict__ seg_off,
            const float4* __restrict__ B4, uint32_t ldb4, int32_t d4, const float* __restrict__ bias, int relu,
-           float* __restrict__ C, int64_t ldc, float* __restrict__ partial, HubView hub, const int4* __restrict__ seg_meta,
-           int32_t* __restrict__ row_cnt /* nullable: segments of a split row that have finished; the last one sums them */) {
+           float* __restrict__ C, int64_t ldc, float* __restrict__ partial, HubView hub, const int4* __restrict__ seg_meta) {
     const int lane = threadIdx.x & 31;
     const int64_t g = ((int64_t)blockIdx.x * SPMM_THREADS + threadIdx.x) >> 5;
-    int32_t s0, s1, il, nseg, kseg = 0;
+    int32_t s0, s1, il, nseg;
     if (seg_meta) {
         if (g >= seg_meta_total(seg_off, n_rows)) return;
         const int4 m = __ldg(seg_meta + g);
-        s0 = m.x; s1 = m.x + (int32_t)((uint32_t)m.y & 511u); il = m.z; nseg = m.w;
-        kseg = (int32_t)((uint32_t)m.y >> 9);
+        s0 = m.x; s1 = m.y; il = m.z; nseg = m.w;
     } else {
         const int32_t total = seg_off[n_rows];
         if (g >= total) return;
@@ -169,40 +164,6 @@ k_spmm_vec(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indic
         for (int q = 0; q < NV; ++q) {
             const int col = lane + 32 * q;
             if (col < d4) dst[col] = acc[q];
-        }
-        if (row_cnt) {
-            // the segment that finishes LAST adds the partial rows in segment order (the order k_spmm_fixup uses, so the bits
-            // are the same whichever segment that is) — no second kernel walks the split rows afterwards
-            __threadfence();
-            int32_t done = 0;
-            if (lane == 0) done = atomicAdd(&row_cnt[il], 1);
-            done = __shfl_sync(LT_FULL, done, 0);
-            if (done == nseg - 1) {
-                __threadfence();
-                const float4* P4 = reinterpret_cast<const float4*>(partial) + ((int64_t)g - kseg) * d4;
-                float* out = C + (int64_t)il * ldc;
-                for (int col = lane; col < d4; col += 32) {
-                    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-                    int32_t sgm = 0;
-                    for (; sgm + 8 <= nseg; sgm += 8) {
-                        float4 p[8];
-#pragma unroll
-                        for (int u = 0; u < 8; ++u) p[u] = __ldcg(P4 + (int64_t)(sgm + u) * d4 + col);
-#pragma unroll
-                        for (int u = 0; u < 8; ++u) { a.x += p[u].x; a.y += p[u].y; a.z += p[u].z; a.w += p[u].w; }
-                    }
-                    for (; sgm < nseg; ++sgm) {
-                        const float4 p = __ldcg(P4 + (int64_t)sgm * d4 + col);
-                        a.x += p.x; a.y += p.y; a.z += p.z; a.w += p.w;
-                    }
-                    if (bias) {
-                        const float4 b = __ldg(reinterpret_cast<const float4*>(bias) + col);
-                        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
-                    }
-                    if (relu) { a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f); }
-                    reinterpret_cast<float4*>(out)[col] = a;
-                }
-            }
         }
     }
 }
@@ -777,19 +738,12 @@ int spmm_csr_f32_seg(const int32_t* indptr, const int32_t* indices, const float*
         if (multi) LT_TRY(scratch.alloc(&partial, (size_t)total_seg * d));
         const unsigned bl = (unsigned)ceil_div(total_seg * 32, SPMM_THREADS);
         int4* seg_meta = nullptr;
-        int32_t* row_cnt = nullptr;
         if (opt(OPT_SPMM_SEGMETA) != 0 && total_seg >= (int64_t)num_sms() * 64) {     // big products: one load per work item
             LT_TRY(scratch.alloc(&seg_meta, (size_t)total_seg));
             k_spmm_segmeta<<<(unsigned)ceil_div(n_list, 256), 256, 0, s>>>(indptr, rows, sel, n_list, seg_off, seg_meta);
             LT_LAUNCH_CHECK();
-            if (multi) {                                                              // split rows are summed by their last segment
-                LT_TRY(scratch.alloc(&row_cnt, (size_t)n_list));
-                LT_CUDA(cudaMemsetAsync(row_cnt, 0, (size_t)n_list * 4, s));
-            }
         }
-        const bool staged_kernel = d4 <= 32 && opt(OPT_SPMM_STAGE) != 0 && total_seg >= (int64_t)num_sms() * 64;
-        if (staged_kernel) row_cnt = nullptr;                                         // the staged variant keeps the fix-up kernel
-#define LT_SPMM_V(NV_, GIF_, MINB_) k_spmm_vec<NV_, GIF_, MINB_, false><<<bl, SPMM_THREADS, 0, s>>>(indptr, indices, values, rows, sel, n_list, seg_off, B4, (uint32_t)(ldb / 4), d4, bias, relu, C, ldc, partial, HubView{nullptr, nullptr, nullptr, 0}, seg_meta, row_cnt)
+#define LT_SPMM_V(NV_, GIF_, MINB_) k_spmm_vec<NV_, GIF_, MINB_, false><<<bl, SPMM_THREADS, 0, s>>>(indptr, indices, values, rows, sel, n_list, seg_off, B4, (uint32_t)(ldb / 4), d4, bias, relu, C, ldc, partial, HubView{nullptr, nullptr, nullptr, 0}, seg_meta)
         // d ≤ 128: 8 gathers in flight per lane at 3 CTAs/SM (no spills) measured best on C5 (2.54 ms; 4 CTAs 2.64,
         // 16 in flight at 2 CTAs 3.16): the kernel then moves its 13.9 GB of DRAM traffic at 84 % of the copy peak
         const bool use_hub = d4 <= 32 && hub && hub->valid;
@@ -828,7 +782,7 @@ int spmm_csr_f32_seg(const int32_t* indptr, const int32_t* indices, const float*
             attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
             LT_CUDA(cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &attr));
             k_spmm_vec<1, 8, 3, true><<<bl, SPMM_THREADS, 0, s>>>(indptr, indices, values, rows, sel, n_list, seg_off, B4,
-                                                                  (uint32_t)(ldb / 4), d4, bias, relu, C, ldc, partial, hub->view, seg_meta, row_cnt);
+                                                                  (uint32_t)(ldb / 4), d4, bias, relu, C, ldc, partial, hub->view, seg_meta);
             attr.accessPolicyWindow.num_bytes = 0;                      // the caller's stream gets its default policy back
             cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &attr);
         }
@@ -838,7 +792,7 @@ int spmm_csr_f32_seg(const int32_t* indptr, const int32_t* indices, const float*
         else LT_SPMM_V(4, 4, 2);
 #undef LT_SPMM_V
         LT_LAUNCH_CHECK();
-        if (multi && !row_cnt) {
+        if (multi) {
             k_spmm_fixup<<<(unsigned)ceil_div((int64_t)n_list, 256), 256, 0, s>>>(seg_off, sel, n_list, partial, d, bias,
                                                                                      relu, C, ldc);
             LT_LAUNCH_CHECK();
