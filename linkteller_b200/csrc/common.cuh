@@ -153,9 +153,10 @@ struct HubView {
     const int32_t* pref;     // [ceil(n/32) + 1] exclusive scan of the words' popcounts: slot of a hub column
     const float4* rows4;     // compact copy of the hub rows, row stride ld4 float4
     uint32_t ld4;
+    const uint32_t* trans;   // [n] float4 offset of column c: HUB_FLAG | slot·ld4 into rows4 for a hub, c·ldb4 into B otherwise
 };
 struct HubPanel {
-    HubView view{nullptr, nullptr, nullptr, 0};
+    HubView view{nullptr, nullptr, nullptr, 0, nullptr};
     void* base = nullptr;    // start and size of the persisting access-policy window
     size_t bytes = 0;
     bool valid = false;

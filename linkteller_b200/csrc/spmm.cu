@@ -63,11 +63,34 @@ constexpr uint32_t HUB_FLAG = 0x80000000u;
 
 template <bool HUB>
 __device__ __forceinline__ uint32_t spmm_offset(int32_t c, uint32_t ldb4, const HubView& hub) {
-    if (HUB) {
-        const uint32_t b = hub.bits[c >> 5], m = 1u << (c & 31);
-        if (b & m) return HUB_FLAG | ((uint32_t)(hub.pref[c >> 5] + __popc(b & (m - 1))) * hub.ld4);
-    }
+    if (HUB) return __ldg(hub.trans + c);            // one lookup in the per-attack translation table (10 MB at n = 2.45 M)
     return (uint32_t)c * ldb4;
+}
+
+// hub offsets of every work item, translated ONCE by a streaming pass (a warp per segment, coalesced) into a table padded
+// to SPMM_SEG entries per segment: the product then reads offsets exactly as it reads column indices — the lookup
+// (bitmap word + prefix, a dependent round trip) leaves the gather loop's critical path.
+__global__ void __launch_bounds__(256)
+k_hub_translate(const int4* __restrict__ seg_meta, const int32_t* __restrict__ seg_off, int32_t n_rows,
+                const int32_t* __restrict__ indices, uint32_t ldb4, HubView hub, uint32_t* __restrict__ pre) {
+    // 8 lanes per segment (the median segment has 48 entries): four segments per warp, eight independent index loads and
+    // eight independent lookups in flight per lane
+    const int sub = threadIdx.x & 7;
+    const int64_t g = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    if (g >= __ldg(seg_off + n_rows)) return;
+    const int4 m = __ldg(seg_meta + g);
+    const int32_t cnt = m.y - m.x;
+    for (int32_t t0 = 0; t0 < cnt; t0 += 64) {
+        int32_t c[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) c[u] = t0 + sub + 8 * u < cnt ? indices[m.x + t0 + sub + 8 * u] : -1;
+        uint32_t o[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) o[u] = c[u] >= 0 ? __ldg(hub.trans + c[u]) : 0u;
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            if (c[u] >= 0) pre[g * SPMM_SEG + t0 + sub + 8 * u] = o[u];
+    }
 }
 
 __device__ __forceinline__ int32_t seg_meta_total(const int32_t* __restrict__ seg_off, int32_t n_rows) { return __ldg(seg_off + n_rows); }
@@ -77,7 +100,8 @@ __global__ void __launch_bounds__(SPMM_THREADS, MINB)
 k_spmm_vec(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices, const float* __restrict__ values,
            const int32_t* __restrict__ rows, const int32_t* __restrict__ sel, int32_t n_rows, const int32_t* __restrict__ seg_off,
            const float4* __restrict__ B4, uint32_t ldb4, int32_t d4, const float* __restrict__ bias, int relu,
-           float* __restrict__ C, int64_t ldc, float* __restrict__ partial, HubView hub, const int4* __restrict__ seg_meta) {
+           float* __restrict__ C, int64_t ldc, float* __restrict__ partial, HubView hub, const int4* __restrict__ seg_meta,
+           const uint32_t* __restrict__ pre = nullptr /* HUB: pre-translated offsets, SPMM_SEG per segment */) {
     const int lane = threadIdx.x & 31;
     const int64_t g = ((int64_t)blockIdx.x * SPMM_THREADS + threadIdx.x) >> 5;
     int32_t s0, s1, il, nseg;
@@ -109,11 +133,12 @@ k_spmm_vec(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indic
     for (int q = 0; q < NV; ++q) Bl[q] = B4 + min(lane + 32 * q, d4 - 1);
     const float4* Hl = HUB ? hub.rows4 + min(lane, d4 - 1) : nullptr;       // HUB ⇒ NV == 1
 
-    uint32_t mo = s0 + lane < s1 ? spmm_offset<HUB>(indices[s0 + lane], ldb4, hub) : 0u;
+    const uint32_t* pre_seg = (HUB && pre) ? pre + g * SPMM_SEG - s0 : nullptr;        // pre_seg[pos] for pos in [s0, s1)
+    uint32_t mo = s0 + lane < s1 ? (pre_seg ? pre_seg[s0 + lane] : spmm_offset<HUB>(indices[s0 + lane], ldb4, hub)) : 0u;
     float mv = s0 + lane < s1 ? values[s0 + lane] : 0.f;
     for (int32_t base = s0; base < s1; base += 32) {
         const int32_t nx = base + 32 + lane;
-        const uint32_t no = nx < s1 ? spmm_offset<HUB>(indices[nx], ldb4, hub) : 0u;
+        const uint32_t no = nx < s1 ? (pre_seg ? pre_seg[nx] : spmm_offset<HUB>(indices[nx], ldb4, hub)) : 0u;
         const float nv = nx < s1 ? values[nx] : 0.f;
         const int cnt = min(32, s1 - base);
         for (int k = 0; k < cnt; k += GIF) {
@@ -557,13 +582,34 @@ k_hub_hist(const int32_t* __restrict__ indptr, int32_t n, int32_t* __restrict__ 
     for (int i = threadIdx.x; i < HUB_BINS; i += blockDim.x)
         if (sh[i]) atomicAdd(&hist[i], sh[i]);
 }
-// thr[0] = smallest degree d with #{deg ≥ d} ≤ kmax (single thread: 4096 bins)
-__global__ void k_hub_pick(const int32_t* __restrict__ hist, int32_t kmax, int32_t* __restrict__ thr) {
-    if (threadIdx.x || blockIdx.x) return;
-    int64_t acc = 0;
-    int d = HUB_BINS;
-    while (d > 1 && acc + hist[d - 1] <= kmax) { acc += hist[d - 1]; --d; }
-    thr[0] = d;            // d == HUB_BINS: not even the top bin fits — no hubs
+// thr[0] = smallest degree d with #{deg ≥ d} ≤ kmax.  One CTA of 1024 threads: suffix sums of the 4096 bins in shared
+// memory (a single thread walking the bins took 252 µs: one dependent global load per bin).
+__global__ void __launch_bounds__(1024)
+k_hub_pick(const int32_t* __restrict__ hist, int32_t kmax, int32_t* __restrict__ thr) {
+    __shared__ int32_t suf[HUB_BINS + 1];            // suf[d] = #{deg ≥ d}
+    __shared__ int32_t blk[1024];
+    const int t = threadIdx.x;
+    // thread t owns bins 4t .. 4t+3
+    const int32_t h0 = hist[4 * t], h1 = hist[4 * t + 1], h2 = hist[4 * t + 2], h3 = hist[4 * t + 3];
+    blk[t] = h0 + h1 + h2 + h3;
+    __syncthreads();
+    // inclusive suffix scan of blk (Hillis-Steele over 1024 entries)
+    for (int o = 1; o < 1024; o <<= 1) {
+        const int32_t add = t + o < 1024 ? blk[t + o] : 0;
+        __syncthreads();
+        blk[t] += add;
+        __syncthreads();
+    }
+    const int32_t above = t + 1 < 1024 ? blk[t + 1] : 0;          // Σ bins ≥ 4(t+1)
+    suf[4 * t + 3] = above + h3;
+    suf[4 * t + 2] = above + h3 + h2;
+    suf[4 * t + 1] = above + h3 + h2 + h1;
+    suf[4 * t] = above + h3 + h2 + h1 + h0;
+    if (t == 0) suf[HUB_BINS] = 0;
+    __syncthreads();
+    // the smallest d ≥ 1 with suf[d] ≤ kmax: suf is non-increasing in d, so exactly one boundary exists
+    for (int d = 1 + t; d <= HUB_BINS; d += 1024)
+        if (suf[d] <= kmax && (d == 1 || suf[d - 1] > kmax)) thr[0] = d;      // d == HUB_BINS: no hubs
 }
 // warp per 32 nodes: membership word + its popcount
 __global__ void __launch_bounds__(256)
@@ -578,6 +624,15 @@ k_hub_bits(const int32_t* __restrict__ indptr, int32_t n, const int32_t* __restr
     const uint32_t b = __ballot_sync(LT_FULL, hub);
     if (lane == 0) { bits[w] = b; cnt[w] = __popc(b); }
 }
+// thread per column: its offset in the product's address space (see HubView::trans)
+__global__ void k_hub_trans(const uint32_t* __restrict__ bits, const int32_t* __restrict__ pref, int32_t n, uint32_t ldb4,
+                            uint32_t ldh4, uint32_t* __restrict__ trans) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    const uint32_t b = bits[c >> 5], m = 1u << (c & 31);
+    trans[c] = (b & m) ? (HUB_FLAG | ((uint32_t)(pref[c >> 5] + __popc(b & (m - 1))) * ldh4)) : (uint32_t)c * ldb4;
+}
+
 // warp per word: copy its hub rows into their slots
 __global__ void __launch_bounds__(256)
 k_hub_copy(const uint32_t* __restrict__ bits, const int32_t* __restrict__ pref, int32_t n_words, const float4* __restrict__ B4,
@@ -652,6 +707,8 @@ int hub_prepare(const int32_t* indptr, int32_t n, const float* B, int64_t ldb, i
     LT_TRY(scratch.alloc(&bits, (size_t)n_words));
     LT_TRY(scratch.alloc(&cnt, (size_t)n_words + 1));
     LT_TRY(scratch.alloc(&pref, (size_t)n_words + 1));
+    uint32_t* trans;
+    LT_TRY(scratch.alloc(&trans, (size_t)n));         // every allocation BEFORE the fork below: the side stream orders after it
     thr = hist + HUB_BINS;
     if (s != scratch.stream) {        // runs on another stream than the one that owns the scratch (and the inputs): order after it
         cudaEvent_t ev;
@@ -665,7 +722,7 @@ int hub_prepare(const int32_t* indptr, int32_t n, const float* B, int64_t ldb, i
     LT_CUDA(cudaMemsetAsync(hist, 0, ((size_t)HUB_BINS + 1) * 4, s));
     k_hub_hist<<<(unsigned)num_sms() * 4, 256, 0, s>>>(indptr, n, hist);
     LT_LAUNCH_CHECK();
-    k_hub_pick<<<1, 32, 0, s>>>(hist, (int32_t)(kmax > n ? n : kmax), thr);
+    k_hub_pick<<<1, 1024, 0, s>>>(hist, (int32_t)(kmax > n ? n : kmax), thr);
     LT_LAUNCH_CHECK();
     k_hub_bits<<<(unsigned)ceil_div((int64_t)n_words * 32, 256), 256, 0, s>>>(indptr, n, thr, bits, cnt, n_words);
     LT_LAUNCH_CHECK();
@@ -673,7 +730,9 @@ int hub_prepare(const int32_t* indptr, int32_t n, const float* B, int64_t ldb, i
     k_hub_copy<<<(unsigned)ceil_div((int64_t)n_words * 32, 256), 256, 0, s>>>(bits, pref, n_words, reinterpret_cast<const float4*>(B),
                                                                            (uint32_t)(ldb / 4), d4, reinterpret_cast<float4*>(panel), ldh4);
     LT_LAUNCH_CHECK();
-    out->view = HubView{bits, pref, reinterpret_cast<const float4*>(panel), ldh4};
+    k_hub_trans<<<(unsigned)ceil_div(n, 256), 256, 0, s>>>(bits, pref, n, (uint32_t)(ldb / 4), ldh4, trans);
+    LT_LAUNCH_CHECK();
+    out->view = HubView{bits, pref, reinterpret_cast<const float4*>(panel), ldh4, trans};
     out->base = panel;
     out->bytes = (size_t)kmax * ldh4 * 16;
     out->valid = true;
@@ -743,7 +802,7 @@ int spmm_csr_f32_seg(const int32_t* indptr, const int32_t* indices, const float*
             k_spmm_segmeta<<<(unsigned)ceil_div(n_list, 256), 256, 0, s>>>(indptr, rows, sel, n_list, seg_off, seg_meta);
             LT_LAUNCH_CHECK();
         }
-#define LT_SPMM_V(NV_, GIF_, MINB_) k_spmm_vec<NV_, GIF_, MINB_, false><<<bl, SPMM_THREADS, 0, s>>>(indptr, indices, values, rows, sel, n_list, seg_off, B4, (uint32_t)(ldb / 4), d4, bias, relu, C, ldc, partial, HubView{nullptr, nullptr, nullptr, 0}, seg_meta)
+#define LT_SPMM_V(NV_, GIF_, MINB_) k_spmm_vec<NV_, GIF_, MINB_, false><<<bl, SPMM_THREADS, 0, s>>>(indptr, indices, values, rows, sel, n_list, seg_off, B4, (uint32_t)(ldb / 4), d4, bias, relu, C, ldc, partial, HubView{nullptr, nullptr, nullptr, 0, nullptr}, seg_meta)
         // d ≤ 128: 8 gathers in flight per lane at 3 CTAs/SM (no spills) measured best on C5 (2.54 ms; 4 CTAs 2.64,
         // 16 in flight at 2 CTAs 3.16): the kernel then moves its 13.9 GB of DRAM traffic at 84 % of the copy peak
         const bool use_hub = d4 <= 32 && hub && hub->valid;
@@ -768,7 +827,7 @@ int spmm_csr_f32_seg(const int32_t* indptr, const int32_t* indices, const float*
                 LT_CUDA(cudaFuncSetAttribute(k_spmm_stage<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 k_spmm_stage<false><<<bls, 32 * STG_WARPS, smem, s>>>(indptr, indices, values, rows, sel, n_list, seg_off, B4,
                                                                       (uint32_t)(ldb / 4), d4, bias, relu, C, ldc, partial,
-                                                                      HubView{nullptr, nullptr, nullptr, 0});
+                                                                      HubView{nullptr, nullptr, nullptr, 0, nullptr});
             }
         }
         else if (use_hub) {
@@ -781,8 +840,15 @@ int spmm_csr_f32_seg(const int32_t* indptr, const int32_t* indices, const float*
             attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
             attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
             LT_CUDA(cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &attr));
+            uint32_t* pre = nullptr;
+            if (seg_meta && opt(OPT_SPMM_HUB) == 1) {                     // 2: look the offsets up inside the product instead
+                LT_TRY(scratch.alloc(&pre, (size_t)total_seg * SPMM_SEG));
+                k_hub_translate<<<(unsigned)ceil_div(total_seg * 8, 256), 256, 0, s>>>(seg_meta, seg_off, n_list, indices,
+                                                                                        (uint32_t)(ldb / 4), hub->view, pre);
+                LT_LAUNCH_CHECK();
+            }
             k_spmm_vec<1, 8, 3, true><<<bl, SPMM_THREADS, 0, s>>>(indptr, indices, values, rows, sel, n_list, seg_off, B4,
-                                                                  (uint32_t)(ldb / 4), d4, bias, relu, C, ldc, partial, hub->view, seg_meta);
+                                                                  (uint32_t)(ldb / 4), d4, bias, relu, C, ldc, partial, hub->view, seg_meta, pre);
             attr.accessPolicyWindow.num_bytes = 0;                      // the caller's stream gets its default policy back
             cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &attr);
         }
