@@ -281,7 +281,7 @@ def main():
         # every rank must take the same branch: agree on whether all of them mapped their peers
         ok = torch.ones(1, device=dev)
         try:
-            comm = attack.make_node_comm(group, T, dev)
+            comm = attack.make_node_comm(group, T, dev, n=wl.n, hidden=wl.h)
         except Exception as e:                                   # no P2P / IPC on this box: NCCL all-gather of the dense rows
             ok.zero_()
             if rank == 0:

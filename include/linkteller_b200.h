@@ -268,8 +268,14 @@ int lt_pair_influence(const int32_t* indptr, const int32_t* indices, const float
  * lt_comm_buffer(comm) holds all T rows.  Every rank must make the call for every attack, also with hi == lo.  Waits are
  * bounded (≈ 2 s); lt_comm_timed_out reports (and clears) a wait that gave up.  Synchronising calls: create, open,
  * timed_out, destroy.
+ * aux_bytes > 0 adds a second symmetric region: with n·(ceil(h/32) + 2)·4 bytes of it lt_attack_efficient_comm also SHARDS
+ * THE RESTRICTED PRECOMPUTE — every rank marks the frontier rows of ALL T test nodes (the same set on every rank), takes
+ * the rank-th 1/world of them through the SpMM and the sign GEMM, stores its 44-byte sign records (sign mask, min and max
+ * |H|) into every rank's aux region and a third flag exchange completes them — instead of every rank re-computing the hub
+ * rows its slice shares with all the others.  (Option "shard_rows" = 0, or an aux region that is too small, keeps the
+ * per-slice precompute.)
  * ------------------------------------------------------------------------------------------- */
-int lt_comm_create(int rank, int world, int64_t bytes, lt_comm** comm_host);
+int lt_comm_create(int rank, int world, int64_t bytes, int64_t aux_bytes, lt_comm** comm_host);
 int lt_comm_get_handle(const lt_comm* comm, void* handle64_host);
 int lt_comm_open(lt_comm* comm, const void* all_handles_host);
 void* lt_comm_buffer(const lt_comm* comm);

@@ -56,7 +56,7 @@ _SIGS = {
     "lt_dp_edgerand_apply": [P, P, P, I32, P, P, I64, P, P, P, I64, P, P],
     "lt_dp_lapgraph_select": [P, P, P, I32, P, I64, P, P, P, I64, P, P],
     "lt_pair_influence": [P, P, P, I32, P, I64, I32, P, P, P, I32, I32, P, I32, P, P, I64, F32, P, P],
-    "lt_comm_create": [INT, INT, I64, P],
+    "lt_comm_create": [INT, INT, I64, I64, P],
     "lt_comm_get_handle": [P, P],
     "lt_comm_open": [P, P],
     "lt_comm_buffer": [P],

@@ -34,9 +34,11 @@ def _world(group):
     return torch.distributed.get_world_size(group), torch.distributed.get_rank(group)
 
 
-def make_node_comm(group, T: int, device) -> ops.NodeComm:
+def make_node_comm(group, T: int, device, n: int = 0, hidden: int = 0) -> ops.NodeComm:
     """Symmetric influence matrices for the ranks of `group` (one node): CUDA IPC handles are exchanged with
-    all_gather_object.  Raises if the peers cannot be mapped (no P2P / IPC): callers then keep the NCCL all-gather."""
+    all_gather_object.  Raises if the peers cannot be mapped (no P2P / IPC): callers then keep the NCCL all-gather.
+    With the graph size `n` and the hidden width the buffers also get room for the frontier rows' sign records, and the
+    ranks shard the restricted precompute by frontier rows instead of each re-computing the shared hub rows."""
     import torch.distributed as dist
     world, rank = dist.get_world_size(group), dist.get_rank(group)
 
@@ -44,7 +46,7 @@ def make_node_comm(group, T: int, device) -> ops.NodeComm:
         got = [None] * world
         dist.all_gather_object(got, mine, group=group)
         return got
-    return ops.NodeComm(rank, world, T, device, exchange)
+    return ops.NodeComm(rank, world, T, device, exchange, n=n, hidden=hidden)
 
 
 def influence_matrix(adj_hat: ops.DeviceCSR, x, w1, b1, w2, test_nodes: torch.Tensor, delta: float,

@@ -61,17 +61,19 @@ using namespace lt;
 
 static size_t comm_payload_aligned(size_t bytes) { return (bytes + 4095) / 4096 * 4096; }
 
-extern "C" int lt_comm_create(int rank, int world, int64_t bytes, lt_comm** comm_host) {
-    LT_CHECK_ARG(comm_host && world >= 1 && world <= LT_MAX_RANKS && rank >= 0 && rank < world && bytes > 0,
-                 "lt_comm_create: need 0 <= rank < world <= 8 and bytes > 0");
+extern "C" int lt_comm_create(int rank, int world, int64_t bytes, int64_t aux_bytes, lt_comm** comm_host) {
+    LT_CHECK_ARG(comm_host && world >= 1 && world <= LT_MAX_RANKS && rank >= 0 && rank < world && bytes > 0 && aux_bytes >= 0,
+                 "lt_comm_create: need 0 <= rank < world <= 8, bytes > 0, aux_bytes >= 0");
     lt_comm* c = new lt_comm();
-    c->rank = rank; c->world = world; c->bytes = (size_t)bytes;
-    const size_t pay = comm_payload_aligned((size_t)bytes);
+    c->rank = rank; c->world = world; c->bytes = (size_t)bytes; c->aux_bytes = (size_t)aux_bytes;
+    const size_t mat = comm_payload_aligned((size_t)bytes);
+    const size_t pay = mat + comm_payload_aligned((size_t)aux_bytes);
     void* base = nullptr;
     cudaError_t e = cudaMalloc(&base, pay + 4096);
     if (e != cudaSuccess) { set_error("lt_comm_create: cudaMalloc(%zu) failed: %s", pay + 4096, cudaGetErrorString(e)); delete c; return LT_ERR_NOMEM; }
     cudaMemset((char*)base + pay, 0, 4096);
     c->peer[rank] = base;
+    c->aux[rank] = (char*)base + mat;
     c->flags[rank] = reinterpret_cast<uint32_t*>((char*)base + pay);
     c->timeout_flag = reinterpret_cast<int*>((char*)base + pay + 2048);
     cudaIpcMemHandle_t h;
@@ -96,7 +98,8 @@ extern "C" int lt_comm_get_handle(const lt_comm* comm, void* handle64_host) {
 // all_handles_host: world x 64 bytes, rank order (the caller exchanges them, e.g. torch.distributed.all_gather_object)
 extern "C" int lt_comm_open(lt_comm* comm, const void* all_handles_host) {
     LT_CHECK_ARG(comm && all_handles_host, "lt_comm_open");
-    const size_t pay = comm_payload_aligned(comm->bytes);
+    const size_t mat = comm_payload_aligned(comm->bytes);
+    const size_t pay = mat + comm_payload_aligned(comm->aux_bytes);
     for (int r = 0; r < comm->world; ++r) {
         if (r == comm->rank) continue;
         cudaIpcMemHandle_t h;
@@ -108,6 +111,7 @@ extern "C" int lt_comm_open(lt_comm* comm, const void* all_handles_host) {
             return LT_ERR_CUDA;
         }
         comm->peer[r] = p;
+        comm->aux[r] = (char*)p + mat;
         comm->flags[r] = reinterpret_cast<uint32_t*>((char*)p + pay);
     }
     comm->opened = true;

@@ -82,7 +82,7 @@ int device_alloc(void** out, size_t bytes, cudaStream_t s);
 // first query (LT_NO_OVERLAP, LT_NO_SIGN_PATH, LT_TC_WS, LT_SPMM_PANEL, LT_SPMM_PANEL_MB, LT_SPMM_PANEL_LMIN,
 // LT_SPMM_HUB, LT_SPMM_HUB_MB, LT_FIX_EPS); after that no call reads the environment.
 enum Opt { OPT_OVERLAP = 0, OPT_SIGN_PATH, OPT_TC_WS, OPT_SPMM_PANEL, OPT_SPMM_PANEL_MB, OPT_SPMM_PANEL_LMIN, OPT_SPMM_HUB,
-           OPT_SPMM_HUB_MB, OPT_FIX_EPS, OPT_SPMM_STAGE, OPT_SPMM_SEGMETA, OPT_COUNT };
+           OPT_SPMM_HUB_MB, OPT_FIX_EPS, OPT_SPMM_STAGE, OPT_SPMM_SEGMETA, OPT_SHARD_ROWS, OPT_COUNT };
 int opt(Opt which);
 
 // ---- phase timers (lt_prof_*): CUDA events on the launching stream, only when enabled ----
@@ -91,6 +91,14 @@ struct ProfScope {
     cudaStream_t stream;
     ProfScope(const char* name, cudaStream_t s);
     ~ProfScope();
+};
+// host wall-clock of a region of library code (enqueue cost / time blocked in a sync), recorded only while the phase
+// timers are on and reported by lt_prof_report as "host_<name> count total_ms"
+struct HostScope {
+    const char* name;
+    long long t0;
+    explicit HostScope(const char* n);
+    ~HostScope();
 };
 int num_sms();
 
@@ -171,16 +179,18 @@ constexpr int LT_MAX_RANKS = 8;
 }  // namespace lt
 struct lt_comm {
     int rank = 0, world = 1;
-    size_t bytes = 0;                      // payload bytes of every rank's buffer
+    size_t bytes = 0;                      // payload bytes of every rank's buffer (the T x T matrix)
+    size_t aux_bytes = 0;                  // second region of every rank's buffer: sign records of the frontier rows (0: none)
     void* peer[lt::LT_MAX_RANKS] = {};     // base of rank r's buffer in THIS process (peer[rank] = the local allocation)
-    uint32_t* flags[lt::LT_MAX_RANKS] = {};  // rank r's flag block: [2][LT_MAX_RANKS] epochs ("zeroed", "rows written") by writer rank
+    void* aux[lt::LT_MAX_RANKS] = {};      // rank r's aux region in THIS process
+    uint32_t* flags[lt::LT_MAX_RANKS] = {};  // rank r's flag block: [3][LT_MAX_RANKS] epochs ("zeroed", "rows written", "signs pushed") by writer rank
     uint32_t epoch = 0;                    // attacks run so far (every rank calls in lock step)
     int* timeout_flag = nullptr;           // device word set by a wait that gave up
     bool opened = false;
     unsigned char handle[64] = {};         // cudaIpcMemHandle_t of the local allocation
 };
 namespace lt {
-int comm_signal(lt_comm* c, int which, cudaStream_t s);   // which: 0 = "my matrix is zero-filled", 1 = "my rows are written"
+int comm_signal(lt_comm* c, int which, cudaStream_t s);   // which: 0 = "my matrix is zero-filled", 1 = "my rows are written", 2 = "my sign records are pushed"
 int comm_wait(lt_comm* c, int which, cudaStream_t s);
 
 // ---- primitives implemented in scan.cu / radix_sort.cu ----

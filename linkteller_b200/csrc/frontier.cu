@@ -63,6 +63,7 @@ struct lt_plan {
     int32_t* seg_off = nullptr;   // [R+1] exclusive scan of the SpMM segment counts of the frontier rows
     int64_t total_seg = -1;       // its total (read back with the other sizes: the restricted SpMM needs no sync of its own)
     int32_t n_groups_host = -1;
+    bool mark_all = false;        // frontier rows of ALL T test nodes, not of the slice (several ranks sharding the precompute)
     bool listed_only = false;     // listed-pair mode (lt_pair_influence): incidences only, no observer lists / records
     void* owned[24];
     int n_owned = 0;
@@ -888,7 +889,10 @@ static int exact_fix_run(int mode, const lt_plan* p, const int32_t* s_row, const
     if (p->n_groups) LT_CUDA(cudaMemcpyAsync(pin.h + 2, p->n_groups, 4, cudaMemcpyDeviceToHost, s));
     LT_CUDA(cudaEventRecord(ev, s));
     LT_TRY(queue_f1());
-    LT_CUDA(cudaEventSynchronize(ev));
+    {
+        HostScope hsync("fix_counters_wait");
+        LT_CUDA(cudaEventSynchronize(ev));
+    }
     const int32_t n_slow = pin.h[0], total_seg = pin.h[1];
     if (p->n_groups && pin.h[2] >= 0) const_cast<lt_plan*>(p)->n_groups_host = pin.h[2];
     if (n_fixed_host) *n_fixed_host = n_slow;
@@ -1008,6 +1012,8 @@ static int plan_build(lt_plan* p, const int32_t* indptr, const int32_t* indices,
     const int32_t n = p->n, T = p->T, lo = p->lo, Ts = p->Ts;
     Scratch scratch(s);
     struct ScopeBox { ProfScope* p; ~ScopeBox() { delete p; } void end() { delete p; p = nullptr; } } prof_a{new ProfScope("plan", s)};
+    HostScope* host_head = new HostScope("plan_head_enqueue");
+    struct HostBox { HostScope*& p; ~HostBox() { delete p; p = nullptr; } } host_head_box{host_head};
     const int32_t n_words = (n + 31) / 32;
     // one zero-filled block: [frontier bitmap | test-node bitmap | Σ segments, Σ nnz (2 x u64) | err]
     uint32_t* zero_blk;
@@ -1026,8 +1032,9 @@ static int plan_build(lt_plan* p, const int32_t* indptr, const int32_t* indices,
     k_test_lens<<<(unsigned)ceil_div(T, 256), 256, 0, s>>>(indptr, test_nodes, T, n, lo, p->hi, all_len, p->s_indptr, err, seen);
     LT_LAUNCH_CHECK();
     LT_TRY(exclusive_scan_i32(p->s_indptr, p->s_indptr, Ts, s));
-    LT_TRY(mark_rows(indptr, indices, test_nodes, n, lo, Ts, p->s_indptr, bits, s));
     LT_TRY(exclusive_scan_i32(all_len, all_len, T, s));
+    if (p->mark_all) LT_TRY(mark_rows(indptr, indices, test_nodes, n, 0, T, all_len, bits, s));     // the same set on every rank
+    else LT_TRY(mark_rows(indptr, indices, test_nodes, n, lo, Ts, p->s_indptr, bits, s));
     k_word_counts<<<(unsigned)ceil_div(n_words, 256), 256, 0, s>>>(bits, n_words, indptr, cnt, seg_tot);
     LT_LAUNCH_CHECK();
     LT_TRY(exclusive_scan_i32(cnt, pref, n_words, s));
@@ -1039,7 +1046,12 @@ static int plan_build(lt_plan* p, const int32_t* indptr, const int32_t* indices,
     LT_CUDA(cudaMemcpyAsync(hs + 5, pref + n_words, 4, cudaMemcpyDeviceToHost, s));
     LT_CUDA(cudaMemcpyAsync(hs + 6, all_len + T, 4, cudaMemcpyDeviceToHost, s));
     LT_CUDA(cudaMemcpyAsync(hs + 7, err, 4, cudaMemcpyDeviceToHost, s));
-    LT_CUDA(cudaStreamSynchronize(s));
+    delete host_head; host_head = nullptr;
+    {
+        HostScope hsync("plan_sync1_wait");
+        LT_CUDA(cudaStreamSynchronize(s));
+    }
+    HostScope host_mid("plan_after_sync1_enqueue");
     int herr = hs[7];
     if (herr & 1) { set_error("lt_plan_create: test node outside [0,%d)", n); return LT_ERR_DATA; }
     if (herr & 2) { set_error("lt_plan_create: duplicate test node"); return LT_ERR_DATA; }
@@ -1075,10 +1087,14 @@ static int plan_build(lt_plan* p, const int32_t* indptr, const int32_t* indices,
     }
     StreamJoin join(s, s2);                     // declared before scratch2: the join runs after scratch2's frees are queued
     prof_a.end();
-    if (early) LT_TRY(early(p, early_ctx, s2));
+    {
+        HostScope he("precompute_enqueue");
+        if (early) LT_TRY(early(p, early_ctx, s2));
+    }
     s = s2;                                     // everything below runs on the side stream (or still on the caller's)
     Scratch scratch2(s);
     ProfScope prof_b(s2 != join.main ? "plan_side" : "plan", s);
+    HostScope host_side("plan_side_total");
     LT_TRY(plan_alloc(p, &p->s_j, (size_t)E, s));
     LT_TRY(plan_alloc(p, &p->s_rho, (size_t)E, s));
     LT_TRY(plan_alloc(p, &p->s_a, (size_t)E, s));
@@ -1128,7 +1144,10 @@ static int plan_build(lt_plan* p, const int32_t* indptr, const int32_t* indices,
     LT_CUDA(cudaMemcpyAsync(&hM, rec_off + E, 8, cudaMemcpyDeviceToHost, s));
     LT_CUDA(cudaMemcpyAsync(&hNB, p->b_indptr + R, 4, cudaMemcpyDeviceToHost, s));
     LT_CUDA(cudaMemcpyAsync(&herr, err, sizeof(int), cudaMemcpyDeviceToHost, s));
-    LT_CUDA(cudaStreamSynchronize(s));
+    {
+        HostScope hsync("plan_sync2_wait");
+        LT_CUDA(cudaStreamSynchronize(s));
+    }
     if (herr & 1) { set_error("lt_plan_create: test node outside [0,%d)", n); return LT_ERR_DATA; }
     if (herr & 2) { set_error("lt_plan_create: duplicate test node"); return LT_ERR_DATA; }
     if (herr & 4) {
@@ -1169,7 +1188,11 @@ static int plan_build(lt_plan* p, const int32_t* indptr, const int32_t* indices,
 // ΔQ[e,:] = ΔR[e,:]·W for every incidence e of the plan (F1).  H row of incidence e = H[h_index[e]]
 // (the plan's compact frontier index by default; node ids when H holds every row), P row = P[p_index ? p_index[j] : j].
 // dq: [E, lddq] with lddq = frontier_lddq(E, h, c).
+// sharded precompute (several ranks): every rank must take the tensor-core / sign-mask path whatever the size of its own
+// slice, or the ranks would disagree about the exchange of sign records — set for the duration of such a call
+static thread_local bool g_force_tc = false;
 static inline bool frontier_use_tc(int64_t E, int32_t h, int32_t c) {
+    if (g_force_tc) return c <= 256 && c >= 8;
     return c <= 256 && c >= 8 && E * (int64_t)h * c >= ((int64_t)1 << 24);
 }
 static inline int32_t frontier_lddq(int64_t E, int32_t h, int32_t c) { return frontier_use_tc(E, h, c) ? (c + 3) / 4 * 4 : c; }
@@ -1787,7 +1810,28 @@ struct AttackCtx {
     HubPanel hub;                       // hot rows of X kept in the L2 for the restricted SpMM (built on the side stream)
     cudaEvent_t hub_ready = nullptr;
     cudaEvent_t pv_ready = nullptr;     // P_v = X[v]·W1 of the slice: started at entry on the side stream, needed by F1 only
+    lt_comm* comm = nullptr;            // several ranks
+    bool shard = false;                 // … that shard the restricted precompute by (global) frontier rows
 };
+
+// This rank's share [r0, r0+Rg) of the sign records → the aux region of every rank: the sign words are already in the local
+// region (the GEMM wrote them there), the min / max |H| of the share come from `minmax` ([0,Rg) min, [Rg,2Rg) max).
+// Layout of an aux region: sign words [R x wpr], min |H| [R], max |H| [R].
+__global__ void k_push_signs(lt_comm c, int32_t R, int32_t wpr, int32_t r0, int32_t Rg, const uint32_t* __restrict__ minmax) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t n_sign = (int64_t)Rg * wpr;
+    if (idx < n_sign) {
+        const int64_t at = (int64_t)r0 * wpr + idx;
+        const uint32_t w = static_cast<const uint32_t*>(c.aux[c.rank])[at];
+        for (int r = 0; r < c.world; ++r)
+            if (r != c.rank) static_cast<uint32_t*>(c.aux[r])[at] = w;
+    } else if (idx < n_sign + 2 * (int64_t)Rg) {
+        const int64_t i = idx - n_sign;                                   // [0,Rg): min, [Rg,2Rg): max
+        const int64_t at = (int64_t)R * wpr + (i < Rg ? r0 + i : (int64_t)R + r0 + (i - Rg));
+        const uint32_t v = minmax[i];
+        for (int r = 0; r < c.world; ++r) static_cast<uint32_t*>(c.aux[r])[at] = v;
+    }
+}
 
 int attack_early(lt_plan* plan, void* vctx, cudaStream_t side) {
     AttackCtx& a = *static_cast<AttackCtx*>(vctx);
@@ -1796,6 +1840,46 @@ int attack_early(lt_plan* plan, void* vctx, cudaStream_t side) {
     const int32_t R = plan->R, Ts = plan->Ts, n = a.n, f = a.f, h = a.h, c = a.c;
     (void)side;
     const bool aggregate_first = (f < h) && (f % 4 == 0) && (a.ldx % 4 == 0) && ((uintptr_t)a.X % 16 == 0);
+    if (a.shard) {
+        // R is the frontier of ALL test nodes here — the same rows, in the same order, on every rank.  Every decision below
+        // depends on global quantities only, so the ranks agree on it.
+        lt_comm* cm = a.comm;
+        const int32_t wpr = (h + 31) / 32;
+        const bool fits = (size_t)R * (wpr + 2) * 4 <= cm->aux_bytes && (int64_t)R * h * f >= ((int64_t)1 << 24) && R >= cm->world;
+        if (fits) {
+            const int32_t r0 = (int32_t)((int64_t)R * cm->rank / cm->world), r1 = (int32_t)((int64_t)R * (cm->rank + 1) / cm->world);
+            const int32_t Rg = r1 - r0;
+            uint32_t* aux = static_cast<uint32_t*>(cm->aux[cm->rank]);
+            uint32_t* minmax;
+            LT_TRY(scratch.alloc(&a.AX, (size_t)Rg * f));
+            LT_TRY(scratch.alloc(&minmax, (size_t)2 * Rg));
+            {
+                ProfScope prof("spmm_ax", s);
+                LT_TRY(spmm_csr_f32_seg(a.indptr, a.indices, a.values, n, plan->rows + r0, Rg, a.X, a.ldx, f, nullptr, 0, a.AX, f,
+                                        nullptr, -1, s));
+            }
+            {
+                ProfScope prof("gemm_h", s);
+                LT_CUDA(cudaMemsetAsync(minmax, 0x7f, (size_t)Rg * 4, s));
+                LT_CUDA(cudaMemsetAsync(minmax + Rg, 0, (size_t)Rg * 4, s));
+                LT_TRY(gemm_3xtf32_signs(a.AX, f, a.W1, h, a.b1, Rg, h, f, aux + (size_t)r0 * wpr, minmax, s));
+            }
+            {
+                ProfScope prof("comm_push_signs", s);
+                const int64_t words = (int64_t)Rg * (wpr + 2);
+                k_push_signs<<<(unsigned)ceil_div(words, 256), 256, 0, s>>>(*cm, R, wpr, r0, Rg, minmax);
+                LT_LAUNCH_CHECK();
+                LT_TRY(comm_signal(cm, 2, s));
+                LT_TRY(comm_wait(cm, 2, s));
+            }
+            a.wpr = wpr;
+            a.signs = aux;
+            a.minabs = aux + (size_t)R * wpr;
+            a.sign_path = true;
+            return LT_OK;
+        }
+        // too small / does not fit: every rank evaluates all R rows itself (redundant, consistent)
+    }
     // sign-mask path: H_R is never written — the GEMM keeps one bit per element and the row's smallest magnitude
     // (36 bytes per frontier row instead of 4h), F1 reads those, and the rows where a ReLU can switch are patched
     a.sign_path = aggregate_first && frontier_use_tc(plan->E, h, c) && h >= 16 && (int64_t)R * h * f >= ((int64_t)1 << 24) &&
@@ -1855,6 +1939,7 @@ static int attack_efficient_impl(const int32_t* indptr, const int32_t* indices, 
                                  int64_t ldx, int32_t f, const float* W1, const float* b1, const float* W2, int32_t h, int32_t c,
                                  const int32_t* test_nodes, int32_t T, int32_t lo, int32_t hi, float delta, float* out, int64_t ldo,
                                  lt_comm* comm, int64_t* info_host, cudaStream_t s, const ListedPairs* listed = nullptr) {
+    HostScope host_all("attack_total");
     lt_plan* plan = new lt_plan();
     plan->n = n; plan->T = T; plan->lo = lo; plan->hi = hi; plan->Ts = hi - lo;
     plan->listed_only = listed != nullptr;
@@ -1926,6 +2011,14 @@ static int attack_efficient_impl(const int32_t* indptr, const int32_t* indices, 
         }
         int32_t n_fixed = 0;
         const bool work = hi > lo;
+        // several ranks with room for the sign records: shard the restricted precompute by frontier rows.  Decided from
+        // quantities every rank sees alike (shapes, alignment, options), so all ranks take the same branch.
+        a.comm = comm;
+        a.shard = comm && comm->world > 1 && comm->aux_bytes > 0 && opt(OPT_SHARD_ROWS) != 0 && !listed && sign_path_enabled() &&
+                  f < h && f % 4 == 0 && ldx % 4 == 0 && (uintptr_t)X % 16 == 0 && (uintptr_t)W1 % 16 == 0 && h >= 16 && c >= 8 &&
+                  c <= 256 && T >= 8 * comm->world;
+        plan->mark_all = a.shard;
+        struct ForceTc { bool on; explicit ForceTc(bool v) : on(v) { if (on) g_force_tc = true; } ~ForceTc() { if (on) g_force_tc = false; } } force_tc(a.shard);
         if (st == LT_OK && work)
             st = plan_build(plan, indptr, indices, values, test_nodes, s, overlap_enabled() ? attack_early : nullptr, &a);
         if (st == LT_OK && work && !overlap_enabled()) st = attack_early(plan, &a, s);

@@ -5,6 +5,7 @@
 #include <string.h>
 
 #include <atomic>
+#include <chrono>
 #include <mutex>
 
 namespace lt {
@@ -19,7 +20,7 @@ const OptDef kOpts[OPT_COUNT] = {
     {"spmm_panel_mb", "LT_SPMM_PANEL_MB", 48, false}, {"spmm_panel_lmin", "LT_SPMM_PANEL_LMIN", 64, false},
     {"spmm_hub", "LT_SPMM_HUB", 0, false},          {"spmm_hub_mb", "LT_SPMM_HUB_MB", 64, false},
     {"fix_eps", "LT_FIX_EPS", 19, false},           {"spmm_stage", "LT_SPMM_STAGE", 0, false},
-    {"spmm_segmeta", "LT_SPMM_SEGMETA", 1, false},
+    {"spmm_segmeta", "LT_SPMM_SEGMETA", 1, false}, {"shard_rows", "LT_SHARD_ROWS", 1, false},
 };
 std::atomic<int> g_opt[OPT_COUNT];
 std::once_flag g_opt_once;
@@ -54,19 +55,42 @@ struct ProfRec { const char* name; cudaEvent_t a, b; };
 constexpr int PROF_MAX = 4096;
 ProfRec g_prof[PROF_MAX];
 int g_prof_n = 0;
+int g_prof_created = 0;      // slots [0, g_prof_created) own a pair of events
 bool g_prof_on = false;
 }  // namespace
 
 ProfScope::ProfScope(const char* name, cudaStream_t s) : slot(-1), stream(s) {
     if (!g_prof_on || g_prof_n >= PROF_MAX) return;
     ProfRec& r = g_prof[g_prof_n];
-    if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
+    // events are created once per slot and reused by later measurements (lt_prof_reset only rewinds): creating two events
+    // per scope cost ~0.1 ms of host time per attack inside the very region being measured
+    if (g_prof_n >= g_prof_created) {
+        if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
+        g_prof_created = g_prof_n + 1;
+    }
     r.name = name;
     slot = g_prof_n++;
     cudaEventRecord(r.a, s);
 }
 ProfScope::~ProfScope() {
     if (slot >= 0) cudaEventRecord(g_prof[slot].b, stream);
+}
+
+namespace {
+struct HostRec { const char* name; int count; double ms; };
+HostRec g_host[64];
+int g_host_n = 0;
+}  // namespace
+static long long now_ns() {
+    return std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+HostScope::HostScope(const char* n) : name(n), t0(g_prof_on ? now_ns() : 0) {}
+HostScope::~HostScope() {
+    if (!t0) return;
+    const double ms = (now_ns() - t0) * 1e-6;
+    for (int i = 0; i < g_host_n; ++i)
+        if (g_host[i].name == name || strcmp(g_host[i].name, name) == 0) { g_host[i].count++; g_host[i].ms += ms; return; }
+    if (g_host_n < 64) g_host[g_host_n++] = HostRec{name, 1, ms};
 }
 
 int num_sms() {
@@ -131,8 +155,8 @@ extern "C" int lt_get_option(const char* name, int* value_host) {
 extern "C" int64_t lt_launch_count(void) { return (int64_t)g_launches; }
 extern "C" int lt_prof_enable(int on) { g_prof_on = on != 0; return LT_OK; }
 extern "C" int lt_prof_reset(void) {
-    for (int i = 0; i < g_prof_n; ++i) { cudaEventDestroy(g_prof[i].a); cudaEventDestroy(g_prof[i].b); }
     g_prof_n = 0;
+    g_host_n = 0;
     return LT_OK;
 }
 extern "C" int lt_prof_report(char* buf_host, int64_t cap) {
@@ -158,6 +182,11 @@ extern "C" int lt_prof_report(char* buf_host, int64_t cap) {
     buf_host[0] = 0;
     for (int k = 0; k < nn; ++k) {
         int w = snprintf(buf_host + off, (size_t)(cap - off), "%s %d %.6f\n", names[k], counts[k], total[k]);
+        if (w < 0 || off + w >= cap) { set_error("lt_prof_report: buffer too small"); return LT_ERR_CAPACITY; }
+        off += w;
+    }
+    for (int k = 0; k < g_host_n; ++k) {
+        int w = snprintf(buf_host + off, (size_t)(cap - off), "host_%s %d %.6f\n", g_host[k].name, g_host[k].count, g_host[k].ms);
         if (w < 0 || off + w >= cap) { set_error("lt_prof_report: buffer too small"); return LT_ERR_CAPACITY; }
         off += w;
     }

@@ -337,13 +337,16 @@ class NodeComm:
     of them from inside its reduce kernel.  `exchange(handle_bytes) -> list of every rank's handle bytes` is the host-side
     channel (attack.make_node_comm uses torch.distributed.all_gather_object)."""
 
-    def __init__(self, rank: int, world: int, T: int, device, exchange):
+    def __init__(self, rank: int, world: int, T: int, device, exchange, n: int = 0, hidden: int = 0):
         lib = _lib.load()
         self.rank, self.world, self.T = rank, world, T
         self.device = torch.device(device)
         self._h = C.c_void_p()
+        # n and hidden given: room for the sign records of up to n frontier rows, which lets the ranks shard the
+        # restricted precompute by frontier rows (lt_comm_create, aux_bytes)
+        aux = n * ((hidden + 31) // 32 + 2) * 4 if n and hidden else 0
         with torch.cuda.device(self.device):
-            _lib.check(lib.lt_comm_create(rank, world, T * T * 4, C.byref(self._h)), "lt_comm_create")
+            _lib.check(lib.lt_comm_create(rank, world, T * T * 4, aux, C.byref(self._h)), "lt_comm_create")
             hb = C.create_string_buffer(64)
             _lib.check(lib.lt_comm_get_handle(self._h, hb), "lt_comm_get_handle")
             handles = exchange(hb.raw)

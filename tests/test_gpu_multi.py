@@ -9,7 +9,7 @@ import torch
 pytestmark = [pytest.mark.gpu, pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs ≥ 2 GPUs")]
 
 
-def _worker(rank, world, port, workload, n_test, ok):
+def _worker(rank, world, port, workload, n_test, f, ok):
     import torch.distributed as dist
     from linkteller_b200 import attack, ops, workloads
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -18,12 +18,19 @@ def _worker(rank, world, port, workload, n_test, ok):
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     group = dist.group.WORLD
-    wl = workloads.make(workload, device=dev, n_test=n_test)
+    wl = workloads.make(workload, device=dev, n_test=n_test, f=f)
     T = wl.T
     full = ops.attack_efficient(wl.adj_hat, wl.x, wl.w1, wl.b1, wl.w2, wl.test_nodes, wl.delta)       # all rows, this GPU alone
-    comm = attack.make_node_comm(group, T, dev)
+    comm = attack.make_node_comm(group, T, dev, n=wl.n, hidden=wl.h)
     good = True
     for rep in range(3):                                                                             # epochs reuse the buffers
+        with ops.profile() as prof:
+            m = attack.influence_matrix(wl.adj_hat, wl.x, wl.w1, wl.b1, wl.w2, wl.test_nodes, wl.delta, group=group, comm=comm)
+            torch.cuda.synchronize()
+        good &= bool(torch.equal(m, full))
+        # f % 4 == 0 and f < h: the ranks shard the restricted precompute by frontier rows and exchange sign records
+        good &= ("comm_push_signs" in prof.report()) == (f is not None)
+    with ops.option("shard_rows", 0):                                                                # per-slice precompute: same bits
         m = attack.influence_matrix(wl.adj_hat, wl.x, wl.w1, wl.b1, wl.w2, wl.test_nodes, wl.delta, group=group, comm=comm)
         torch.cuda.synchronize()
         good &= bool(torch.equal(m, full))
@@ -46,11 +53,12 @@ def _worker(rank, world, port, workload, n_test, ok):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("workload,n_test", [("ppi", 500), ("small", 7)])      # even slices, ragged slices (7 rows over 2+ ranks)
-def test_sharded_attack_through_peer_memory_equals_one_gpu(workload, n_test):
+# PPI shape with f = 52 (sharded precompute + sign exchange), PPI as is (f = 50: per-slice precompute), ragged slices
+@pytest.mark.parametrize("workload,n_test,f", [("ppi", 500, 52), ("ppi", 500, None), ("small", 7, None)])
+def test_sharded_attack_through_peer_memory_equals_one_gpu(workload, n_test, f):
     import torch.multiprocessing as mp
     world = min(torch.cuda.device_count(), 8)
     ok = mp.get_context("spawn").Array("i", [0] * world)
     port = 29600 + (os.getpid() + n_test) % 300
-    mp.spawn(_worker, args=(world, port, workload, n_test, ok), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, workload, n_test, f, ok), nprocs=world, join=True)
     assert list(ok) == [1] * world
