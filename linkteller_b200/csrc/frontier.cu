@@ -969,6 +969,24 @@ static int plan_alloc(lt_plan* p, T** out, size_t count, cudaStream_t s) {
     return plan_own(p, q);
 }
 
+// One stream-ordered allocation carved into the plan's arrays: the plan needs ~20 device arrays whose sizes become known
+// at its two host syncs; allocating them one by one cost ~40 driver calls per attack, and at 8 GPUs (kernels of a few µs)
+// the attack is bound by exactly that host time.
+struct PlanArena {
+    char* base = nullptr;
+    size_t off = 0, cap = 0;
+    static size_t pad(size_t b) { return (b + 255) / 256 * 256; }
+    template <typename T>
+    void want(size_t count) { cap += pad((count ? count : 1) * sizeof(T)); }
+    int commit(lt_plan* p, cudaStream_t s) { return plan_alloc(p, &base, cap ? cap : 256, s); }
+    template <typename T>
+    T* take(size_t count) {
+        T* q = reinterpret_cast<T*>(base + off);
+        off += pad((count ? count : 1) * sizeof(T));
+        return q;
+    }
+};
+
 // A high-priority side stream per device (created once): the second half of the plan runs on it while the restricted
 // SpMM — which only needs the compacted frontier rows — already occupies the caller's stream.
 static cudaStream_t side_stream() {
@@ -1063,8 +1081,15 @@ static int plan_build(lt_plan* p, const int32_t* indptr, const int32_t* indices,
     const int32_t R = p->R;
     const int64_t E = p->E;
 
-    LT_TRY(plan_alloc(p, &p->rows, (size_t)R, s));
-    LT_TRY(plan_alloc(p, &p->seg_off, (size_t)R + 1, s));
+    PlanArena ar1;                                  // everything whose size the first sync settled (R, E, Σ test-node degrees)
+    ar1.want<int32_t>((size_t)R); ar1.want<int32_t>((size_t)R + 1);
+    ar1.want<int32_t>((size_t)E); ar1.want<int32_t>((size_t)E); ar1.want<float>((size_t)E);
+    ar1.want<int32_t>((size_t)R + 1); ar1.want<int32_t>((size_t)R + 1);
+    ar1.want<int32_t>((size_t)nb_cap); ar1.want<float>((size_t)nb_cap);
+    ar1.want<int32_t>((size_t)E + 1); ar1.want<int64_t>((size_t)E + 1);
+    LT_TRY(ar1.commit(p, s));
+    p->rows = ar1.take<int32_t>((size_t)R);
+    p->seg_off = ar1.take<int32_t>((size_t)R + 1);
     k_compact_rows<<<(unsigned)ceil_div(n_words, 256), 256, 0, s>>>(bits, pref, n_words, indptr, p->rows, p->seg_off);
     LT_LAUNCH_CHECK();
     LT_TRY(exclusive_scan_i32(p->seg_off, p->seg_off, R, s));
@@ -1095,9 +1120,9 @@ static int plan_build(lt_plan* p, const int32_t* indptr, const int32_t* indices,
     Scratch scratch2(s);
     ProfScope prof_b(s2 != join.main ? "plan_side" : "plan", s);
     HostScope host_side("plan_side_total");
-    LT_TRY(plan_alloc(p, &p->s_j, (size_t)E, s));
-    LT_TRY(plan_alloc(p, &p->s_rho, (size_t)E, s));
-    LT_TRY(plan_alloc(p, &p->s_a, (size_t)E, s));
+    p->s_j = ar1.take<int32_t>((size_t)E);
+    p->s_rho = ar1.take<int32_t>((size_t)E);
+    p->s_a = ar1.take<float>((size_t)E);
     if (E) {
         k_fill_S<<<(unsigned)ceil_div(E, 256), 256, 0, s>>>(indptr, indices, values, test_nodes, lo, Ts, E, bits, pref,
                                                             p->s_indptr, p->s_j, p->s_rho, p->s_a, err);
@@ -1116,10 +1141,10 @@ static int plan_build(lt_plan* p, const int32_t* indptr, const int32_t* indices,
 
     // observers
     int32_t* cursor;
-    LT_TRY(plan_alloc(p, &p->b_indptr, (size_t)R + 1, s));
-    LT_TRY(scratch2.alloc(&cursor, (size_t)R + 1));
-    LT_TRY(plan_alloc(p, &p->b_i, (size_t)nb_cap, s));
-    LT_TRY(plan_alloc(p, &p->b_w, (size_t)nb_cap, s));
+    p->b_indptr = ar1.take<int32_t>((size_t)R + 1);
+    cursor = ar1.take<int32_t>((size_t)R + 1);
+    p->b_i = ar1.take<int32_t>((size_t)nb_cap);
+    p->b_w = ar1.take<float>((size_t)nb_cap);
     LT_CUDA(cudaMemsetAsync(p->b_indptr, 0, ((size_t)R + 1) * 4, s));
     const unsigned blT = (unsigned)ceil_div(nb_cap > 0 ? nb_cap : 1, 256);
     k_observers<0><<<blT, 256, 0, s>>>(indptr, indices, values, test_nodes, T, all_len, bits, pref, p->b_indptr, nullptr, nullptr);
@@ -1132,8 +1157,8 @@ static int plan_build(lt_plan* p, const int32_t* indptr, const int32_t* indices,
     // records
     int32_t* rc;
     int64_t* rec_off;
-    LT_TRY(scratch2.alloc(&rc, (size_t)E + 1));
-    LT_TRY(scratch2.alloc(&rec_off, (size_t)E + 1));
+    rc = ar1.take<int32_t>((size_t)E + 1);
+    rec_off = ar1.take<int64_t>((size_t)E + 1);
     if (E) {
         k_rec_counts<<<(unsigned)ceil_div(E, 256), 256, 0, s>>>(p->s_rho, E, p->b_indptr, rc);
         LT_LAUNCH_CHECK();
@@ -1158,22 +1183,25 @@ static int plan_build(lt_plan* p, const int32_t* indptr, const int32_t* indices,
     p->NB = hNB;
     if (hM >= ((int64_t)1 << 31)) { set_error("lt_plan_create: %lld records exceed 2^31", (long long)hM); return LT_ERR_CAPACITY; }
     const int64_t M = hM;
-    LT_TRY(plan_alloc(p, &p->rec_key, (size_t)M, s));
-    LT_TRY(plan_alloc(p, &p->rec_val, (size_t)M, s));
-    LT_TRY(plan_alloc(p, &p->grp_off, (size_t)M + 2, s));
-    LT_TRY(plan_alloc(p, &p->n_groups, 1, s));
-    LT_TRY(plan_alloc(p, &p->big, (size_t)(M / F2_BIG + 1), s));
-    LT_TRY(plan_alloc(p, &p->n_big, 1, s));
-    LT_CUDA(cudaMemsetAsync(p->n_groups, 0, 4, s));
-    LT_CUDA(cudaMemsetAsync(p->n_big, 0, 4, s));
+    PlanArena ar2;                                  // everything sized by the record count
+    ar2.want<uint64_t>((size_t)M); ar2.want<uint64_t>((size_t)M); ar2.want<int32_t>((size_t)M + 2); ar2.want<int32_t>(2);
+    ar2.want<int32_t>((size_t)(M / F2_BIG + 1)); ar2.want<int32_t>((size_t)M + 1);
+    LT_TRY(ar2.commit(p, s));
+    p->rec_key = ar2.take<uint64_t>((size_t)M);
+    p->rec_val = ar2.take<uint64_t>((size_t)M);
+    p->grp_off = ar2.take<int32_t>((size_t)M + 2);
+    p->n_groups = ar2.take<int32_t>(2);
+    p->n_big = p->n_groups + 1;
+    p->big = ar2.take<int32_t>((size_t)(M / F2_BIG + 1));
+    int32_t* head_buf = ar2.take<int32_t>((size_t)M + 1);
+    LT_CUDA(cudaMemsetAsync(p->n_groups, 0, 8, s));
     if (M) {
         k_expand<<<(unsigned)ceil_div(E, 256), 256, 0, s>>>(p->s_j, p->s_rho, E, p->b_indptr, p->b_i, p->b_w,
                                                                rec_off, p->rec_key, p->rec_val);
         LT_LAUNCH_CHECK();
         BitRange ranges[2] = {{0, bits_for((uint64_t)(T - 1))}, {32, 32 + bits_for((uint64_t)(Ts > 1 ? Ts - 1 : 1))}};
         LT_TRY(radix_sort_u64(p->rec_key, p->rec_val, M, ranges, Ts > 1 ? 2 : 1, s));
-        int32_t* head;
-        LT_TRY(scratch2.alloc(&head, (size_t)M + 1));
+        int32_t* head = head_buf;
         k_rec_heads<<<(unsigned)ceil_div(M, 256), 256, 0, s>>>(p->rec_key, M, head);
         LT_LAUNCH_CHECK();
         LT_TRY(exclusive_scan_i32(head, head, M, s));
@@ -1814,6 +1842,12 @@ struct AttackCtx {
     bool shard = false;                 // … that shard the restricted precompute by (global) frontier rows
 };
 
+// seg_rel[i] = seg_off[i] − seg_off[0] for i ≤ n: the SpMM work-item offsets of a share of the (globally scanned) rows
+__global__ void k_rebase(const int32_t* __restrict__ seg_off, int32_t n, int32_t* __restrict__ seg_rel) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i <= n) seg_rel[i] = seg_off[i] - seg_off[0];
+}
+
 // This rank's share [r0, r0+Rg) of the sign records → the aux region of every rank: the sign words are already in the local
 // region (the GEMM wrote them there), the min / max |H| of the share come from `minmax` ([0,Rg) min, [Rg,2Rg) max).
 // Layout of an aux region: sign words [R x wpr], min |H| [R], max |H| [R].
@@ -1851,12 +1885,20 @@ int attack_early(lt_plan* plan, void* vctx, cudaStream_t side) {
             const int32_t Rg = r1 - r0;
             uint32_t* aux = static_cast<uint32_t*>(cm->aux[cm->rank]);
             uint32_t* minmax;
+            int32_t* seg_rel;
             LT_TRY(scratch.alloc(&a.AX, (size_t)Rg * f));
             LT_TRY(scratch.alloc(&minmax, (size_t)2 * Rg));
+            LT_TRY(scratch.alloc(&seg_rel, (size_t)Rg + 1));
             {
+                // the share's work items: the global offsets rebased; their number is not on the host, so the grid and the
+                // partial-sum buffer take an upper bound (the share holds at most the global count minus one item per other
+                // row) and the surplus warps leave at once — cheaper than a host round trip for the exact number
                 ProfScope prof("spmm_ax", s);
+                k_rebase<<<(unsigned)ceil_div((int64_t)Rg + 1, 256), 256, 0, s>>>(plan->seg_off + r0, Rg, seg_rel);
+                LT_LAUNCH_CHECK();
+                const int64_t bound = plan->total_seg - (int64_t)(R - Rg);
                 LT_TRY(spmm_csr_f32_seg(a.indptr, a.indices, a.values, n, plan->rows + r0, Rg, a.X, a.ldx, f, nullptr, 0, a.AX, f,
-                                        nullptr, -1, s));
+                                        seg_rel, bound, s));
             }
             {
                 ProfScope prof("gemm_h", s);

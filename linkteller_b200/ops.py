@@ -323,6 +323,8 @@ def attack_efficient(adj: DeviceCSR, x, w1, b1, w2, test_nodes: torch.Tensor, de
     else:
         _chk(out, torch.float32, "out", 2)
     info = (C.c_int64 * 8)()
+    if hi == lo:                                    # an empty slice (more ranks than test nodes): nothing to compute
+        return (out, dict(zip(INFO_KEYS, [0] * 8))) if want_info else out
     _lib.check(lib.lt_attack_efficient(_p(adj.indptr), _p(adj.indices), _p(adj.values), n, _p(x), ldx, f, _p(w1),
                                        _p(b1), _p(w2), h, c, _p(test_nodes), T, lo, hi, float(delta), _p(out),
                                        out.stride(0), info if want_info else None, _stream()), "lt_attack_efficient")
