@@ -383,6 +383,19 @@ def main():
                "d2h_bytes_per_step": int(d2h), "steps": k_e2e, "ms_per_step": ems / k_e2e}
         del stage, host
 
+    # several GPUs: the matrix the ranks assembled together must equal, bit for bit, what ONE GPU computes for all T rows
+    # (that single-GPU path is the one checked against the float64 oracle at N = 1 and in tests/test_gpu_large.py)
+    multi_parity = None
+    if world > 1 and not args.no_parity:
+        together = step().clone()
+        alone = ops.attack_efficient(wl.adj_hat, wl.x, wl.w1, wl.b1, wl.w2, wl.test_nodes, wl.delta)
+        torch.cuda.synchronize()
+        same = torch.tensor([int(torch.equal(together, alone))], device=dev)
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        multi_parity = {"equal_to_single_gpu_bitwise": bool(same.item()), "ranks": world, "rows": T,
+                        "note": "every rank compared the jointly assembled T x T matrix with its own single-GPU run of all rows"}
+        del together, alone
+
     if rank == 0:
         peak, peak_src = peaks()
         h, c, f = wl.h, wl.c, wl.f
@@ -465,6 +478,8 @@ def main():
             step()
             torch.cuda.synchronize()
             line.update(cpu_legs(wl, info, out, args))
+        if world > 1:
+            line["parity_check"] = multi_parity           # computed by every rank above (collective-free), rank 0 reports
         print(json.dumps(line), flush=True)
     if world > 1:
         if comm is not None:
