@@ -198,6 +198,10 @@ int comm_wait(lt_comm* c, int which, cudaStream_t s);
 int exclusive_scan_i32(const int32_t* in, int32_t* out, int64_t n, cudaStream_t s);
 int exclusive_scan_i64(const int64_t* in, int64_t* out, int64_t n, cudaStream_t s);
 int exclusive_scan_i32_to_i64(const int32_t* in, int64_t* out, int64_t n, cudaStream_t s);
+// the plan's frontier bitmap: popcount prefix per word + Σ SpMM segments / nnz of the marked rows, one launch
+size_t frontier_word_scan_desc(int32_t n_words);
+int frontier_word_scan(const uint32_t* bits, int32_t n_words, const int32_t* indptr, int32_t* pref, unsigned long long* desc,
+                       unsigned long long* tot, int32_t* R_out, cudaStream_t s);
 
 // Stable LSD radix sort of 64-bit keys over the given bit ranges (8-bit digits), optional 64-bit
 // payload.  Sorted data ends in keys / vals (in place from the caller's view).

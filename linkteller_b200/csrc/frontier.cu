@@ -95,6 +95,77 @@ __global__ void k_test_lens(const int32_t* __restrict__ indptr, const int32_t* _
     if (s_len && i >= lo && i < hi) s_len[i - lo] = len;
 }
 
+// The same for the attack's plan, with both exclusive scans done in place by ONE CTA (T is a few thousand: three
+// launches on the serial head of every attack otherwise): all_off[T+1] over all test nodes, s_indptr[Ts+1] over the
+// slice [lo,hi); sizes[0] = E (Σ slice lengths), sizes[2] = Σ all lengths, sizes[3] |= error bits.
+constexpr int TL_THREADS = 1024, TL_ITEMS = 8;
+__global__ void __launch_bounds__(TL_THREADS)
+k_test_lens_scan(const int32_t* __restrict__ indptr, const int32_t* __restrict__ test_nodes, int32_t T, int32_t n, int32_t lo,
+                 int32_t hi, int32_t* __restrict__ all_off, int32_t* __restrict__ s_indptr, int32_t* __restrict__ sizes,
+                 uint32_t* __restrict__ seen) {
+    __shared__ int32_t wa[32], ws[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int32_t carry_a = 0, carry_s = 0;
+    int* err = sizes + 3;
+    for (int32_t tile = 0; tile < T; tile += TL_THREADS * TL_ITEMS) {
+        const int32_t base = tile + (int32_t)threadIdx.x * TL_ITEMS;
+        int32_t v[TL_ITEMS], len[TL_ITEMS];
+#pragma unroll
+        for (int k = 0; k < TL_ITEMS; ++k) v[k] = base + k < T ? test_nodes[base + k] : -1;
+        int32_t sa = 0, ss = 0;
+#pragma unroll
+        for (int k = 0; k < TL_ITEMS; ++k) {
+            const int32_t i = base + k;
+            int32_t l = 0;
+            if (i < T) {
+                const bool ok = v[k] >= 0 && v[k] < n;
+                if (!ok) atomicOr(err, 1);
+                else {
+                    if (atomicOr(&seen[v[k] >> 5], 1u << (v[k] & 31)) & (1u << (v[k] & 31))) atomicOr(err, 2);   // duplicate
+                    l = indptr[v[k] + 1] - indptr[v[k]];
+                }
+            }
+            len[k] = l;
+            sa += l;
+            if (i >= lo && i < hi) ss += l;
+        }
+        const int32_t ia = warp_inclusive_scan(sa), is = warp_inclusive_scan(ss);
+        if (lane == 31) { wa[warp] = ia; ws[warp] = is; }
+        __syncthreads();
+        if (warp == 0) {
+            const int32_t ta = wa[lane], ts = ws[lane];
+            const int32_t xa = warp_inclusive_scan(ta), xs = warp_inclusive_scan(ts);
+            wa[lane] = xa - ta;                                  // exclusive prefix of the warp
+            ws[lane] = xs - ts;
+        }
+        __syncthreads();
+        int32_t pa = carry_a + wa[warp] + ia - sa, ps = carry_s + ws[warp] + is - ss;
+#pragma unroll
+        for (int k = 0; k < TL_ITEMS; ++k) {
+            const int32_t i = base + k;
+            if (i < T) {
+                all_off[i] = pa;
+                if (i >= lo && i < hi) s_indptr[i - lo] = ps;
+            }
+            pa += len[k];
+            if (i >= lo && i < hi) ps += len[k];
+        }
+        // totals of the tile: the last thread's running values
+        __shared__ int32_t tot_a, tot_s;
+        if (threadIdx.x == TL_THREADS - 1) { tot_a = pa; tot_s = ps; }
+        __syncthreads();
+        carry_a = tot_a;
+        carry_s = tot_s;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        all_off[T] = carry_a;
+        s_indptr[hi - lo] = carry_s;
+        sizes[0] = carry_s;
+        sizes[2] = carry_a;
+    }
+}
+
 // one thread per incidence e = (j, k-th entry of row v_j): set the bit of r.  (A warp per row left the kernel waiting
 // for the few test nodes with thousands of neighbours: 58 µs against 8.)
 __global__ void k_mark_rows(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
@@ -115,36 +186,6 @@ static int mark_rows(const int32_t* indptr, const int32_t* indices, const int32_
     k_mark_rows<<<(unsigned)num_sms() * 16, 256, 0, s>>>(indptr, indices, test_nodes, n, lo, Ts, s_indptr, bits);
     LT_LAUNCH_CHECK();
     return LT_OK;
-}
-
-// thread per word: its popcount; Σ over the marked rows of their SpMM segment counts and of their lengths (one atomic
-// pair per CTA) — known before the first host sync, so the restricted SpMM can be launched right after the compaction
-__global__ void __launch_bounds__(256)
-k_word_counts(const uint32_t* __restrict__ bits, int32_t n_words, const int32_t* __restrict__ indptr, int32_t* __restrict__ cnt,
-              unsigned long long* __restrict__ tot) {
-    const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned long long seg = 0, nnz = 0;
-    if (w < n_words) {
-        uint32_t b = bits[w];
-        cnt[w] = __popc(b);
-        while (b) {
-            const int32_t r = (int32_t)(w * 32) + __ffs(b) - 1;
-            b &= b - 1;
-            const int32_t len = indptr[r + 1] - indptr[r];
-            seg += len <= SPMM_SEG ? 1 : (len + SPMM_SEG - 1) / SPMM_SEG;
-            nnz += len;
-        }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { seg += __shfl_xor_sync(LT_FULL, seg, o); nnz += __shfl_xor_sync(LT_FULL, nnz, o); }
-    __shared__ unsigned long long sh[2][8];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (lane == 0) { sh[0][warp] = seg; sh[1][warp] = nnz; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int k = 1; k < 8; ++k) { seg += sh[0][k]; nnz += sh[1][k]; }
-        if (seg | nnz) { atomicAdd(&tot[0], seg); atomicAdd(&tot[1], nnz); }
-    }
 }
 
 // thread per word: rows[pref + k] = node id of its k-th set bit; nseg = SpMM segments of that row
@@ -1033,37 +1074,34 @@ static int plan_build(lt_plan* p, const int32_t* indptr, const int32_t* indices,
     HostScope* host_head = new HostScope("plan_head_enqueue");
     struct HostBox { HostScope*& p; ~HostBox() { delete p; p = nullptr; } } host_head_box{host_head};
     const int32_t n_words = (n + 31) / 32;
-    // one zero-filled block: [frontier bitmap | test-node bitmap | Σ segments, Σ nnz (2 x u64) | err]
+    // one zero-filled block: [frontier bitmap | test-node bitmap | sizes (8 words) | look-back descriptors of the word scan].
+    // sizes = Σ segments, Σ nnz (2 x u64) | E | R | Σ all lens | err: what the first read-back needs, contiguous, so it
+    // is ONE 32-byte copy; the head of the plan is memset + 3 kernels + that copy.
     uint32_t* zero_blk;
-    int32_t *all_len, *cnt, *pref;
-    const size_t zero_words = (size_t)2 * n_words + 6;
+    int32_t *all_len, *pref;
+    const size_t desc_words = 2 * frontier_word_scan_desc(n_words);
+    const size_t zero_words = (size_t)2 * n_words + 8 + desc_words;
     LT_TRY(scratch.alloc(&zero_blk, zero_words));
     LT_TRY(scratch.alloc(&all_len, (size_t)T + 1));
-    LT_TRY(scratch.alloc(&cnt, (size_t)n_words + 1));
     LT_TRY(scratch.alloc(&pref, (size_t)n_words + 1));
     uint32_t* bits = zero_blk;
     uint32_t* seen = zero_blk + n_words;
-    unsigned long long* seg_tot = reinterpret_cast<unsigned long long*>(zero_blk + 2 * (size_t)n_words);   // word offset 2·n_words: 8-byte aligned
-    int* err = reinterpret_cast<int*>(zero_blk + zero_words - 1);
+    uint32_t* sizes = zero_blk + 2 * (size_t)n_words;                                  // word offset 2·n_words: 8-byte aligned
+    unsigned long long* seg_tot = reinterpret_cast<unsigned long long*>(sizes);
+    unsigned long long* scan_desc = reinterpret_cast<unsigned long long*>(sizes + 8);
+    int* err = reinterpret_cast<int*>(sizes + 7);
     LT_TRY(plan_alloc(p, &p->s_indptr, (size_t)Ts + 1, s));
     LT_CUDA(cudaMemsetAsync(zero_blk, 0, zero_words * 4, s));
-    k_test_lens<<<(unsigned)ceil_div(T, 256), 256, 0, s>>>(indptr, test_nodes, T, n, lo, p->hi, all_len, p->s_indptr, err, seen);
+    k_test_lens_scan<<<1, TL_THREADS, 0, s>>>(indptr, test_nodes, T, n, lo, p->hi, all_len, p->s_indptr,
+                                              reinterpret_cast<int32_t*>(sizes + 4), seen);
     LT_LAUNCH_CHECK();
-    LT_TRY(exclusive_scan_i32(p->s_indptr, p->s_indptr, Ts, s));
-    LT_TRY(exclusive_scan_i32(all_len, all_len, T, s));
     if (p->mark_all) LT_TRY(mark_rows(indptr, indices, test_nodes, n, 0, T, all_len, bits, s));     // the same set on every rank
     else LT_TRY(mark_rows(indptr, indices, test_nodes, n, lo, Ts, p->s_indptr, bits, s));
-    k_word_counts<<<(unsigned)ceil_div(n_words, 256), 256, 0, s>>>(bits, n_words, indptr, cnt, seg_tot);
-    LT_LAUNCH_CHECK();
-    LT_TRY(exclusive_scan_i32(cnt, pref, n_words, s));
+    LT_TRY(frontier_word_scan(bits, n_words, indptr, pref, scan_desc, seg_tot, reinterpret_cast<int32_t*>(sizes + 5), s));
     static thread_local FixPinned pin;              // pinned landing zone of the size read-back
     if (!pin.h) LT_CUDA(cudaHostAlloc((void**)&pin.h, 64, cudaHostAllocDefault));
     int32_t* hs = pin.h;                            // [0..3] Σ seg, Σ nnz (2 x u64) | [4] E | [5] R | [6] Σ all lens | [7] err
-    LT_CUDA(cudaMemcpyAsync(hs, seg_tot, 16, cudaMemcpyDeviceToHost, s));
-    LT_CUDA(cudaMemcpyAsync(hs + 4, p->s_indptr + Ts, 4, cudaMemcpyDeviceToHost, s));
-    LT_CUDA(cudaMemcpyAsync(hs + 5, pref + n_words, 4, cudaMemcpyDeviceToHost, s));
-    LT_CUDA(cudaMemcpyAsync(hs + 6, all_len + T, 4, cudaMemcpyDeviceToHost, s));
-    LT_CUDA(cudaMemcpyAsync(hs + 7, err, 4, cudaMemcpyDeviceToHost, s));
+    LT_CUDA(cudaMemcpyAsync(hs, sizes, 32, cudaMemcpyDeviceToHost, s));
     delete host_head; host_head = nullptr;
     {
         HostScope hsync("plan_sync1_wait");
@@ -1164,15 +1202,18 @@ static int plan_build(lt_plan* p, const int32_t* indptr, const int32_t* indices,
         LT_LAUNCH_CHECK();
     }
     LT_TRY(exclusive_scan_i32_to_i64(rc, rec_off, E, s));
-    int64_t hM = 0;
-    int32_t hNB = 0;
-    LT_CUDA(cudaMemcpyAsync(&hM, rec_off + E, 8, cudaMemcpyDeviceToHost, s));
-    LT_CUDA(cudaMemcpyAsync(&hNB, p->b_indptr + R, 4, cudaMemcpyDeviceToHost, s));
-    LT_CUDA(cudaMemcpyAsync(&herr, err, sizeof(int), cudaMemcpyDeviceToHost, s));
+    // second read-back, into the pinned block too (a copy to pageable memory makes the host wait three times)
+    LT_CUDA(cudaMemcpyAsync(hs + 8, rec_off + E, 8, cudaMemcpyDeviceToHost, s));
+    LT_CUDA(cudaMemcpyAsync(hs + 10, p->b_indptr + R, 4, cudaMemcpyDeviceToHost, s));
+    LT_CUDA(cudaMemcpyAsync(hs + 11, err, sizeof(int), cudaMemcpyDeviceToHost, s));
     {
         HostScope hsync("plan_sync2_wait");
         LT_CUDA(cudaStreamSynchronize(s));
     }
+    int64_t hM;
+    memcpy(&hM, hs + 8, 8);
+    const int32_t hNB = hs[10];
+    herr = hs[11];
     if (herr & 1) { set_error("lt_plan_create: test node outside [0,%d)", n); return LT_ERR_DATA; }
     if (herr & 2) { set_error("lt_plan_create: duplicate test node"); return LT_ERR_DATA; }
     if (herr & 4) {

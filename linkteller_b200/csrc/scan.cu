@@ -108,22 +108,67 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_small(const TI* in, int64
 // scans of the plan — about twenty per attack.
 constexpr uint32_t LB_AGGREGATE = 1u, LB_INCLUSIVE = 2u;
 
+// The value of element i comes from a loader (plain int32 input, or something computed on the fly — the plan's frontier
+// bitmap words), ITEMS consecutive elements per thread.
+struct LoadI32 {
+    const int32_t* in;
+    __device__ __forceinline__ int32_t operator()(int64_t i) { return in[i]; }
+    __device__ __forceinline__ void finish() {}
+};
+
+// element w = popcount of word w of the frontier bitmap; on the side, Σ over the marked rows of their SpMM segment counts
+// and of their lengths (one atomic pair per CTA) — all the first host read-back of the plan needs, in one launch
+struct LoadFrontierWords {
+    const uint32_t* bits;
+    const int32_t* indptr;
+    unsigned long long* tot;               // [0] Σ segments, [1] Σ nnz
+    unsigned long long seg = 0, nnz = 0;
+    __device__ __forceinline__ int32_t operator()(int64_t w) {
+        uint32_t b = bits[w];
+        const int32_t c = __popc(b);
+        while (b) {
+            const int32_t r = (int32_t)(w * 32) + __ffs(b) - 1;
+            b &= b - 1;
+            const int32_t len = indptr[r + 1] - indptr[r];
+            seg += len <= SPMM_SEG ? 1 : (len + SPMM_SEG - 1) / SPMM_SEG;
+            nnz += len;
+        }
+        return c;
+    }
+    __device__ __forceinline__ void finish() {         // every thread of the CTA calls
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { seg += __shfl_xor_sync(LT_FULL, seg, o); nnz += __shfl_xor_sync(LT_FULL, nnz, o); }
+        __shared__ unsigned long long sh[2][SCAN_THREADS / 32];
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        if (lane == 0) { sh[0][warp] = seg; sh[1][warp] = nnz; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int k = 1; k < SCAN_THREADS / 32; ++k) { seg += sh[0][k]; nnz += sh[1][k]; }
+            if (seg | nnz) { atomicAdd(&tot[0], seg); atomicAdd(&tot[1], nnz); }
+        }
+    }
+};
+
+template <typename Load, int ITEMS>
 __global__ void __launch_bounds__(SCAN_THREADS)
-k_scan_lookback(const int32_t* in, int64_t n_in, int32_t* out, int64_t n_out, unsigned long long* desc /* [0] = tile counter */) {
+k_scan_lookback(Load load, int64_t n_in, int32_t* out, int64_t n_out, unsigned long long* desc /* [0] = tile counter */,
+                int32_t* total_out /* nullable: also receives out[n_in] */) {
+    constexpr int TILE = SCAN_THREADS * ITEMS;
     __shared__ int32_t tile_s, prefix_s;
     if (threadIdx.x == 0) tile_s = (int32_t)atomicAdd(desc, 1ull);
     __syncthreads();
     const int32_t tile = tile_s;
     unsigned long long* d = desc + 1;
-    const int64_t base = (int64_t)tile * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
-    int32_t v[SCAN_ITEMS];
+    const int64_t base = (int64_t)tile * TILE + (int64_t)threadIdx.x * ITEMS;
+    int32_t v[ITEMS];
     int32_t sum = 0;
 #pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; ++k) {
+    for (int k = 0; k < ITEMS; ++k) {
         const int64_t i = base + k;
-        v[k] = (i < n_in) ? in[i] : 0;
+        v[k] = (i < n_in) ? load(i) : 0;
         sum += v[k];
     }
+    load.finish();
     int32_t total;
     int32_t pre = block_exclusive_scan<int32_t>(sum, total);
     if (threadIdx.x < 32) {
@@ -155,9 +200,10 @@ k_scan_lookback(const int32_t* in, int64_t n_in, int32_t* out, int64_t n_out, un
     __syncthreads();
     pre += prefix_s;
 #pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; ++k) {
+    for (int k = 0; k < ITEMS; ++k) {
         const int64_t i = base + k;
         if (i < n_out) out[i] = pre;
+        if (total_out && i == n_in) *total_out = pre;
         pre += v[k];
     }
 }
@@ -178,8 +224,8 @@ static int scan_impl(const TI* in, TO* out, int64_t n_in, cudaStream_t s) {
         unsigned long long* desc = nullptr;
         LT_TRY(scratch.alloc(&desc, (size_t)blocks + 1));
         LT_CUDA(cudaMemsetAsync(desc, 0, ((size_t)blocks + 1) * 8, s));
-        k_scan_lookback<<<(unsigned)blocks, SCAN_THREADS, 0, s>>>(reinterpret_cast<const int32_t*>(in), n_in,
-                                                                   reinterpret_cast<int32_t*>(out), n_out, desc);
+        k_scan_lookback<LoadI32, SCAN_ITEMS><<<(unsigned)blocks, SCAN_THREADS, 0, s>>>(
+            LoadI32{reinterpret_cast<const int32_t*>(in)}, n_in, reinterpret_cast<int32_t*>(out), n_out, desc, nullptr);
         LT_LAUNCH_CHECK();
         return LT_OK;
     }
@@ -189,6 +235,19 @@ static int scan_impl(const TI* in, TO* out, int64_t n_in, cudaStream_t s) {
     LT_LAUNCH_CHECK();
     LT_TRY((scan_impl<TO, TO>(sums, sums, blocks, s)));
     k_scan_down<TI, TO><<<(unsigned)blocks, SCAN_THREADS, 0, s>>>(in, n_in, out, n_out, sums);
+    LT_LAUNCH_CHECK();
+    return LT_OK;
+}
+
+// pref[w] = number of frontier rows in the words before w (pref[n_words] = R, also written to *R_out); tot += (Σ segments,
+// Σ nnz) of the marked rows.  desc: frontier_word_scan_desc(n_words) zero-filled 64-bit words.  One word per thread: a
+// thread walks up to 32 rows of its word, wider tiles would serialise that.
+size_t frontier_word_scan_desc(int32_t n_words) { return (size_t)ceil_div((int64_t)n_words + 1, SCAN_THREADS) + 1; }
+int frontier_word_scan(const uint32_t* bits, int32_t n_words, const int32_t* indptr, int32_t* pref, unsigned long long* desc,
+                       unsigned long long* tot, int32_t* R_out, cudaStream_t s) {
+    const int64_t blocks = ceil_div((int64_t)n_words + 1, SCAN_THREADS);
+    k_scan_lookback<LoadFrontierWords, 1><<<(unsigned)blocks, SCAN_THREADS, 0, s>>>(LoadFrontierWords{bits, indptr, tot}, n_words,
+                                                                                     pref, (int64_t)n_words + 1, desc, R_out);
     LT_LAUNCH_CHECK();
     return LT_OK;
 }
