@@ -4,6 +4,7 @@
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o gather_ceiling gather_ceiling.cu && ./gather_ceiling
 #include <cstdio>
 #include <cstdint>
+#include <cstdlib>
 #include <vector>
 #include <cuda_runtime.h>
 
@@ -50,8 +51,11 @@ static void run(const uint32_t* idx, int64_t n_idx, const float4* B4, uint32_t l
     printf("GIF=%2d ctas/SM=%d  %.3f ms  %.0f GB/s (%.2f M rows)\n", GIF, ctas_per_sm, ms, bytes / ms / 1e6, per * nw / 1e6);
 }
 
-int main() {
-    const int64_t n = 2449029; const int d4 = 25; const uint32_t ld4 = 25;
+// optional argument: the row stride of B in float4 units (25 = packed 400-byte rows; 26 = 416 B, rows start on a 32-byte
+// sector boundary; 32 = 512 B) — does aligning the rows buy anything?
+int main(int argc, char** argv) {
+    const int64_t n = 2449029; const int d4 = 25; const uint32_t ld4 = argc > 1 ? (uint32_t)atoi(argv[1]) : 25;
+    printf("row stride %u B\n", ld4 * 16);
     const int64_t n_idx = 31284977;                       // gathers of one C5 attack
     int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
     std::vector<uint32_t> h(n_idx);
@@ -61,6 +65,6 @@ int main() {
     cudaMalloc(&idx, n_idx * 4); cudaMalloc(&B4, n * ld4 * 16); cudaMalloc(&out, (size_t)sms * 8 * 8 * 32 * 16);
     cudaMemcpy(idx, h.data(), n_idx * 4, cudaMemcpyHostToDevice);
     cudaMemset(B4, 0, n * ld4 * 16);
-    for (int c : {2, 3, 4, 6, 8}) { run<4>(idx, n_idx, B4, ld4, d4, out, c, sms); run<8>(idx, n_idx, B4, ld4, d4, out, c, sms); run<16>(idx, n_idx, B4, ld4, d4, out, c, sms); }
+    for (int c : (argc > 1 ? std::vector<int>{3, 4} : std::vector<int>{2, 3, 4, 6, 8})) { run<4>(idx, n_idx, B4, ld4, d4, out, c, sms); run<8>(idx, n_idx, B4, ld4, d4, out, c, sms); run<16>(idx, n_idx, B4, ld4, d4, out, c, sms); }
     return 0;
 }
