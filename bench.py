@@ -114,7 +114,7 @@ class ClockSampler:
 # ncu --set full captures committed under profiles/ (never measured inside a bench run: a run under ncu
 # is not a bench value).  Keyed by (workload, n_gpus, kernel family).
 NCU_TRAFFIC = {
-    ("large", 1, "spmm_ax"): (13.748901e9 + 0.162670e9, "profiles/r2q_ncu_large_summary.txt"),
+    ("large", 1, "spmm_ax"): (12.955522e9 + 0.153716e9, "profiles/r3g_ncu_spmm_summary.txt"),
 }
 
 

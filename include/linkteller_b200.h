@@ -296,7 +296,11 @@ int lt_attack_efficient_comm(const int32_t* indptr, const int32_t* indices, cons
  * in the restricted SpMM, 0), "spmm_hub_mb" (size of the pinned hub panel in MB, 64), "fix_eps" (the float64 fix-up of
  * lt_attack_efficient treats |H| ≤ 2^-fix_eps·max(f,64)/64·max|H[r,:]| as undecidable in float32 and re-evaluates it; 19),
  * "spmm_stage" (cp.async shared-memory staging of the gathered rows, 0), "spmm_segmeta" (work-item table instead of a
- * binary search in the restricted SpMM, 1).
+ * binary search in the restricted SpMM, 1), "shard_rows" (several ranks: restricted precompute sharded by global frontier
+ * rows, 1), "spmm_hint" (L2 eviction-priority hints for the gathers of the restricted SpMM, chosen from the entry values —
+ * 1/sqrt(d_r·d_c) says how hot column c is; 0 off, 2 = hot evict_last / cold evict_first, default 2; results do not
+ * depend on it), "spmm_hint_deg" (column degree from which a row counts as hot; 0 = measured from the degree histogram
+ * so that the hot rows fill spmm_hub_mb, default 0).
  * ------------------------------------------------------------------------------------------- */
 int lt_set_option(const char* name_host, int value);
 int lt_get_option(const char* name_host, int* value_host);

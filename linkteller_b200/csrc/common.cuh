@@ -82,7 +82,7 @@ int device_alloc(void** out, size_t bytes, cudaStream_t s);
 // first query (LT_NO_OVERLAP, LT_NO_SIGN_PATH, LT_TC_WS, LT_SPMM_PANEL, LT_SPMM_PANEL_MB, LT_SPMM_PANEL_LMIN,
 // LT_SPMM_HUB, LT_SPMM_HUB_MB, LT_FIX_EPS); after that no call reads the environment.
 enum Opt { OPT_OVERLAP = 0, OPT_SIGN_PATH, OPT_TC_WS, OPT_SPMM_PANEL, OPT_SPMM_PANEL_MB, OPT_SPMM_PANEL_LMIN, OPT_SPMM_HUB,
-           OPT_SPMM_HUB_MB, OPT_FIX_EPS, OPT_SPMM_STAGE, OPT_SPMM_SEGMETA, OPT_SHARD_ROWS, OPT_COUNT };
+           OPT_SPMM_HUB_MB, OPT_FIX_EPS, OPT_SPMM_STAGE, OPT_SPMM_SEGMETA, OPT_SHARD_ROWS, OPT_SPMM_HINT, OPT_SPMM_HINT_DEG, OPT_COUNT };
 int opt(Opt which);
 
 // ---- phase timers (lt_prof_*): CUDA events on the launching stream, only when enabled ----
@@ -171,6 +171,7 @@ struct HubPanel {
 };
 struct Scratch;
 bool hub_applicable(int32_t n_cols, int64_t ldb, int32_t d, const float* B);
+float spmm_hint_degree(const int32_t* indptr, int32_t n, const float* B, int64_t ldb, int32_t d, cudaStream_t s);
 int hub_prepare(const int32_t* indptr, int32_t n, const float* B, int64_t ldb, int32_t d, HubPanel* out, Scratch& scratch,
                 cudaStream_t s);
 

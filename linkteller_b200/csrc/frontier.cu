@@ -35,7 +35,7 @@ int spmm_csr_f32(const int32_t* indptr, const int32_t* indices, const float* val
 int spmm_csr_f32_seg(const int32_t* indptr, const int32_t* indices, const float* values, int32_t n_cols,
                      const int32_t* rows, int32_t n_rows, const float* B, int64_t ldb, int32_t d, const float* bias, int relu,
                      float* C, int64_t ldc, const int32_t* seg_off_known, int64_t total_seg_known, cudaStream_t s,
-                     const HubPanel* hub = nullptr);
+                     const HubPanel* hub = nullptr, float hint_deg = 0.f);
 
 }  // namespace lt
 
@@ -1877,6 +1877,7 @@ struct AttackCtx {
     uint32_t *signs = nullptr, *minabs = nullptr;
     int32_t wpr = 0;
     HubPanel hub;                       // hot rows of X kept in the L2 for the restricted SpMM (built on the side stream)
+    float hint_deg = 0.f;               // column degree from which a gathered X row is hinted evict_last (0: no hints)
     cudaEvent_t hub_ready = nullptr;
     cudaEvent_t pv_ready = nullptr;     // P_v = X[v]·W1 of the slice: started at entry on the side stream, needed by F1 only
     lt_comm* comm = nullptr;            // several ranks
@@ -1939,7 +1940,7 @@ int attack_early(lt_plan* plan, void* vctx, cudaStream_t side) {
                 LT_LAUNCH_CHECK();
                 const int64_t bound = plan->total_seg - (int64_t)(R - Rg);
                 LT_TRY(spmm_csr_f32_seg(a.indptr, a.indices, a.values, n, plan->rows + r0, Rg, a.X, a.ldx, f, nullptr, 0, a.AX, f,
-                                        seg_rel, bound, s));
+                                        seg_rel, bound, s, nullptr, a.hint_deg));
             }
             {
                 ProfScope prof("gemm_h", s);
@@ -1974,7 +1975,7 @@ int attack_early(lt_plan* plan, void* vctx, cudaStream_t side) {
         {
             ProfScope prof("spmm_ax", s);
             LT_TRY(spmm_csr_f32_seg(a.indptr, a.indices, a.values, n, plan->rows, R, a.X, a.ldx, f, nullptr, 0, a.AX, f,
-                                    plan->seg_off, plan->total_seg, s, a.hub.valid ? &a.hub : nullptr));
+                                    plan->seg_off, plan->total_seg, s, a.hub.valid ? &a.hub : nullptr, a.hint_deg));
         }
         ProfScope prof("gemm_h", s);
         if (a.sign_path) {
@@ -2079,6 +2080,9 @@ static int attack_efficient_impl(const int32_t* indptr, const int32_t* indices, 
                 set_error("lt_attack_efficient: event failed"); st = LT_ERR_CUDA;
             }
         }
+        // eviction-priority hints of the aggregate-first SpMM: the degree threshold (remembered per graph: no device work
+        // after the first attack on it)
+        if (st == LT_OK && hi > lo && f < h && T >= 1024) a.hint_deg = spmm_hint_degree(indptr, n, X, ldx, f, s);
         // hub panel of X for the aggregate-first SpMM: built next to the plan head, on the side stream
         if (st == LT_OK && hi > lo && f < h && hub_applicable(n, ldx, f, X) && T >= 1024) {
             cudaStream_t sd = overlap_enabled() ? side_stream() : nullptr;

@@ -21,6 +21,7 @@ const OptDef kOpts[OPT_COUNT] = {
     {"spmm_hub", "LT_SPMM_HUB", 0, false},          {"spmm_hub_mb", "LT_SPMM_HUB_MB", 64, false},
     {"fix_eps", "LT_FIX_EPS", 19, false},           {"spmm_stage", "LT_SPMM_STAGE", 0, false},
     {"spmm_segmeta", "LT_SPMM_SEGMETA", 1, false}, {"shard_rows", "LT_SHARD_ROWS", 1, false},
+    {"spmm_hint", "LT_SPMM_HINT", 2, false},       {"spmm_hint_deg", "LT_SPMM_HINT_DEG", 0, false},
 };
 std::atomic<int> g_opt[OPT_COUNT];
 std::once_flag g_opt_once;

@@ -95,13 +95,24 @@ k_hub_translate(const int4* __restrict__ seg_meta, const int32_t* __restrict__ s
 
 __device__ __forceinline__ int32_t seg_meta_total(const int32_t* __restrict__ seg_off, int32_t n_rows) { return __ldg(seg_off + n_rows); }
 
-template <int NV, int GIF, int MINB, bool HUB>   // GIF = gathers in flight per lane, MINB = resident CTAs per SM asked of ptxas
+// L2 eviction-priority hints chosen from the VALUE of the entry (HUB == 2): under the symmetric normalisation
+// Â[r,c] = 1/sqrt(d_r·d_c) the value read next to the column index already says how often column c is gathered
+// (d_c = 1/(v²·d_r)), so a gather can be marked evict_last (hot: d_c ≥ hint_deg) or left alone without any lookup.
+// A hint only — wrong guesses (other normalisations) cost cache efficiency, never correctness.
+__device__ __forceinline__ float4 ldg_hint(const float4* p, uint64_t pol) {
+    float4 r;
+    asm("ld.global.nc.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p), "l"(pol));
+    return r;
+}
+
+template <int NV, int GIF, int MINB, int HUB>   // GIF = gathers in flight per lane, MINB = resident CTAs per SM asked of ptxas
 __global__ void __launch_bounds__(SPMM_THREADS, MINB)
 k_spmm_vec(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices, const float* __restrict__ values,
            const int32_t* __restrict__ rows, const int32_t* __restrict__ sel, int32_t n_rows, const int32_t* __restrict__ seg_off,
            const float4* __restrict__ B4, uint32_t ldb4, int32_t d4, const float* __restrict__ bias, int relu,
            float* __restrict__ C, int64_t ldc, float* __restrict__ partial, HubView hub, const int4* __restrict__ seg_meta,
-           const uint32_t* __restrict__ pre = nullptr /* HUB: pre-translated offsets, SPMM_SEG per segment */) {
+           const uint32_t* __restrict__ pre = nullptr /* HUB: pre-translated offsets, SPMM_SEG per segment */,
+           float hint_deg = 0.f, int hint_cold = 0) {
     const int lane = threadIdx.x & 31;
     const int64_t g = ((int64_t)blockIdx.x * SPMM_THREADS + threadIdx.x) >> 5;
     int32_t s0, s1, il, nseg;
@@ -131,15 +142,27 @@ k_spmm_vec(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indic
     const float4* Bl[NV];
 #pragma unroll
     for (int q = 0; q < NV; ++q) Bl[q] = B4 + min(lane + 32 * q, d4 - 1);
-    const float4* Hl = HUB ? hub.rows4 + min(lane, d4 - 1) : nullptr;       // HUB ⇒ NV == 1
+    const float4* Hl = HUB == 1 ? hub.rows4 + min(lane, d4 - 1) : nullptr;       // HUB ⇒ NV == 1
 
-    const uint32_t* pre_seg = (HUB && pre) ? pre + g * SPMM_SEG - s0 : nullptr;        // pre_seg[pos] for pos in [s0, s1)
-    uint32_t mo = s0 + lane < s1 ? (pre_seg ? pre_seg[s0 + lane] : spmm_offset<HUB>(indices[s0 + lane], ldb4, hub)) : 0u;
+    uint64_t pol_hot = 0, pol_cold = 0;
+    float hot_scale = 0.f;                   // hot ⇔ v²·d_r·hint_deg ≤ 1 (d_r: the row's length; split rows: their segment count x SPMM_SEG)
+    if (HUB == 2) {
+        if (hint_cold == 3) { asm("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol_hot)); hint_cold = 1; }
+        else asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_hot));
+        if (hint_cold == 1) asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_cold));
+        else if (hint_cold == 2) asm("createpolicy.fractional.L2::evict_unchanged.b64 %0, 1.0;" : "=l"(pol_cold));
+        else asm("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol_cold));
+        hot_scale = (float)(nseg == 1 ? max(s1 - s0 - 1, 1) : nseg * SPMM_SEG) * hint_deg;
+    }
+    const uint32_t* pre_seg = (HUB == 1 && pre) ? pre + g * SPMM_SEG - s0 : nullptr;        // pre_seg[pos] for pos in [s0, s1)
     float mv = s0 + lane < s1 ? values[s0 + lane] : 0.f;
+    uint32_t mo = s0 + lane < s1 ? (pre_seg ? pre_seg[s0 + lane] : spmm_offset<HUB == 1>(indices[s0 + lane], ldb4, hub)) : 0u;
+    if (HUB == 2 && s0 + lane < s1 && mv * mv * hot_scale <= 1.f) mo |= HUB_FLAG;
     for (int32_t base = s0; base < s1; base += 32) {
         const int32_t nx = base + 32 + lane;
-        const uint32_t no = nx < s1 ? (pre_seg ? pre_seg[nx] : spmm_offset<HUB>(indices[nx], ldb4, hub)) : 0u;
+        uint32_t no = nx < s1 ? (pre_seg ? pre_seg[nx] : spmm_offset<HUB == 1>(indices[nx], ldb4, hub)) : 0u;
         const float nv = nx < s1 ? values[nx] : 0.f;
+        if (HUB == 2 && nx < s1 && nv * nv * hot_scale <= 1.f) no |= HUB_FLAG;
         const int cnt = min(32, s1 - base);
         for (int k = 0; k < cnt; k += GIF) {
             // every load is unconditional and lands in its own register: entries past the end of the row
@@ -148,8 +171,10 @@ k_spmm_vec(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indic
 #pragma unroll
             for (int u = 0; u < GIF; ++u) {
                 const uint32_t o = __shfl_sync(LT_FULL, mo, (k + u) & 31);
-                if (HUB) {
+                if (HUB == 1) {
                     x[u][0] = __ldg(((o & HUB_FLAG) ? Hl : Bl[0]) + (o & ~HUB_FLAG));
+                } else if (HUB == 2) {
+                    x[u][0] = ldg_hint(Bl[0] + (o & ~HUB_FLAG), (o & HUB_FLAG) ? pol_hot : pol_cold);
                 } else {
 #pragma unroll
                     for (int q = 0; q < NV; ++q) x[u][q] = __ldg(Bl[q] + o);
@@ -664,6 +689,48 @@ bool hub_applicable(int32_t n_cols, int64_t ldb, int32_t d, const float* B) {
            (int64_t)n_cols * d * 4 >= ((int64_t)256 << 20) && (int64_t)n_cols * (ldb / 4) < ((int64_t)1 << 31);
 }
 
+// The degree from which a column's row of B counts as hot for the eviction-priority hints of the restricted product:
+// the smallest degree d with #{columns of degree ≥ d}·(bytes a gathered row costs) ≤ spmm_hub_mb (64 MB, half the L2).
+// Â is symmetric on this path, so row lengths are column counts.  0: no hints (option off, B fits the L2, shapes the
+// hinted kernel does not take).  "spmm_hint_deg" > 0 fixes the value; otherwise it is measured ONCE per (indptr, n, d)
+// from a degree histogram — one 4-byte read-back — and remembered: a stale entry (another graph at a recycled address)
+// can only misplace hints, never change a result.
+float spmm_hint_degree(const int32_t* indptr, int32_t n, const float* B, int64_t ldb, int32_t d, cudaStream_t s) {
+    if (opt(OPT_SPMM_HINT) == 0 || d % 4 != 0 || d > 128 || ldb % 4 != 0 || (uintptr_t)B % 16 != 0 ||
+        (int64_t)n * d * 4 < ((int64_t)256 << 20) || (int64_t)n * (ldb / 4) >= ((int64_t)1 << 31))
+        return 0.f;
+    const int fixed = opt(OPT_SPMM_HINT_DEG);
+    if (fixed > 0) return (float)fixed;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0.f;
+    const int mb = opt(OPT_SPMM_HUB_MB);
+    struct Entry { const void* indptr; int32_t n, d; int mb, dev; float deg; };
+    static Entry cache[8];
+    static int next = 0;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
+    for (const Entry& e : cache)
+        if (e.indptr == indptr && e.n == n && e.d == d && e.mb == mb && e.dev == dev) return e.deg;
+    float deg = 0.f;
+    int32_t* hist = nullptr;
+    if (cudaMallocAsync((void**)&hist, ((size_t)HUB_BINS + 1) * 4, s) == cudaSuccess) {
+        const int64_t row_bytes = ((int64_t)d * 4 + 63) / 64 * 64 + 48;        // 64-byte DRAM granules, unaligned start
+        const int64_t kmax = ((int64_t)mb << 20) / row_bytes;
+        int32_t thr = HUB_BINS;
+        cudaMemsetAsync(hist, 0, ((size_t)HUB_BINS + 1) * 4, s);
+        k_hub_hist<<<(unsigned)num_sms() * 4, 256, 0, s>>>(indptr, n, hist);
+        k_hub_pick<<<1, 1024, 0, s>>>(hist, (int32_t)(kmax > n ? n : kmax), hist + HUB_BINS);
+        const bool ok = cudaMemcpyAsync(&thr, hist + HUB_BINS, 4, cudaMemcpyDeviceToHost, s) == cudaSuccess &&
+                        cudaStreamSynchronize(s) == cudaSuccess;
+        cudaFreeAsync(hist, s);
+        if (ok && thr > 1 && thr < HUB_BINS) deg = (float)thr;
+    }
+    cudaGetLastError();
+    cache[next] = Entry{indptr, n, d, mb, dev, deg};
+    next = (next + 1) % 8;
+    return deg;
+}
+
 // Builds the panel for B on stream s.  bits / pref live in `scratch` (they must outlive the product); the panel rows live
 // in a per-device buffer the library keeps (the second persistent allocation besides lt_plan: the persisting L2 lines
 // must keep their address from one attack to the next, or stale lines would occupy the set-aside region).
@@ -746,7 +813,7 @@ int hub_prepare(const int32_t* indptr, int32_t n, const float* B, int64_t ldb, i
 int spmm_csr_f32_seg(const int32_t* indptr, const int32_t* indices, const float* values, int32_t n_cols,
                      const int32_t* rows, int32_t n_rows, const float* B, int64_t ldb, int32_t d, const float* bias, int relu,
                      float* C, int64_t ldc, const int32_t* seg_off_known, int64_t total_seg_known, cudaStream_t s,
-                     const HubPanel* hub = nullptr);
+                     const HubPanel* hub = nullptr, float hint_deg = 0.f);
 
 int spmm_csr_f32(const int32_t* indptr, const int32_t* indices, const float* values, int32_t n_cols,
                  const int32_t* rows, int32_t n_rows, const float* B, int64_t ldb, int32_t d, const float* bias, int relu,
@@ -757,7 +824,7 @@ int spmm_csr_f32(const int32_t* indptr, const int32_t* indices, const float* val
 int spmm_csr_f32_seg(const int32_t* indptr, const int32_t* indices, const float* values, int32_t n_cols,
                      const int32_t* rows, int32_t n_rows, const float* B, int64_t ldb, int32_t d, const float* bias, int relu,
                      float* C, int64_t ldc, const int32_t* seg_off_known, int64_t total_seg_known, cudaStream_t s,
-                     const HubPanel* hub) {
+                     const HubPanel* hub, float hint_deg) {
     if (n_rows == 0 || d == 0) return LT_OK;
     const bool vec = (d % 4 == 0) && (ldb % 4 == 0) && (ldc % 4 == 0) && d <= 512 && (int64_t)n_cols * (ldb / 4) < ((int64_t)1 << 32) &&
                      ((uintptr_t)B % 16 == 0) && ((uintptr_t)C % 16 == 0) && (!bias || (uintptr_t)bias % 16 == 0);
@@ -802,7 +869,7 @@ int spmm_csr_f32_seg(const int32_t* indptr, const int32_t* indices, const float*
             k_spmm_segmeta<<<(unsigned)ceil_div(n_list, 256), 256, 0, s>>>(indptr, rows, sel, n_list, seg_off, seg_meta);
             LT_LAUNCH_CHECK();
         }
-#define LT_SPMM_V(NV_, GIF_, MINB_) k_spmm_vec<NV_, GIF_, MINB_, false><<<bl, SPMM_THREADS, 0, s>>>(indptr, indices, values, rows, sel, n_list, seg_off, B4, (uint32_t)(ldb / 4), d4, bias, relu, C, ldc, partial, HubView{nullptr, nullptr, nullptr, 0, nullptr}, seg_meta)
+#define LT_SPMM_V(NV_, GIF_, MINB_) k_spmm_vec<NV_, GIF_, MINB_, 0><<<bl, SPMM_THREADS, 0, s>>>(indptr, indices, values, rows, sel, n_list, seg_off, B4, (uint32_t)(ldb / 4), d4, bias, relu, C, ldc, partial, HubView{nullptr, nullptr, nullptr, 0, nullptr}, seg_meta)
         // d ≤ 128: 8 gathers in flight per lane at 3 CTAs/SM (no spills) measured best on C5 (2.54 ms; 4 CTAs 2.64,
         // 16 in flight at 2 CTAs 3.16): the kernel then moves its 13.9 GB of DRAM traffic at 84 % of the copy peak
         const bool use_hub = d4 <= 32 && hub && hub->valid;
@@ -847,10 +914,18 @@ int spmm_csr_f32_seg(const int32_t* indptr, const int32_t* indices, const float*
                                                                                         (uint32_t)(ldb / 4), hub->view, pre);
                 LT_LAUNCH_CHECK();
             }
-            k_spmm_vec<1, 8, 3, true><<<bl, SPMM_THREADS, 0, s>>>(indptr, indices, values, rows, sel, n_list, seg_off, B4,
+            k_spmm_vec<1, 8, 3, 1><<<bl, SPMM_THREADS, 0, s>>>(indptr, indices, values, rows, sel, n_list, seg_off, B4,
                                                                   (uint32_t)(ldb / 4), d4, bias, relu, C, ldc, partial, hub->view, seg_meta, pre);
             attr.accessPolicyWindow.num_bytes = 0;                      // the caller's stream gets its default policy back
             cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &attr);
+        }
+        else if (d4 <= 32 && hint_deg > 0.f && opt(OPT_SPMM_HINT) != 0 && seg_meta && (int64_t)n_cols * (ldb / 4) < ((int64_t)1 << 31)) {
+            // value-derived eviction-priority hints (see ldg_hint).  spmm_hint = 1: cold gathers evict_normal, 2 (default):
+            // evict_first, 3: evict_unchanged, 4: evict_first with the hot gathers left evict_normal
+            k_spmm_vec<1, 8, 3, 2><<<bl, SPMM_THREADS, 0, s>>>(indptr, indices, values, rows, sel, n_list, seg_off, B4,
+                                                               (uint32_t)(ldb / 4), d4, bias, relu, C, ldc, partial,
+                                                               HubView{nullptr, nullptr, nullptr, 0, nullptr}, seg_meta, nullptr,
+                                                               hint_deg, opt(OPT_SPMM_HINT) - 1);
         }
         else if (d4 <= 32) LT_SPMM_V(1, 8, 3);
         else if (d4 <= 64) LT_SPMM_V(2, 4, 4);

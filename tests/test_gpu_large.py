@@ -61,7 +61,7 @@ def test_large_whole_matrix_properties(large):
 
 
 def test_large_spmm_variants_give_the_same_bits(large):
-    """The restricted SpMM has three opt-in variants kept for the record: hub rows of X gathered from an
+    """The restricted SpMM has opt-in variants kept for the record: hub rows of X gathered from an
     L2-resident panel under a persisting access-policy window ("spmm_hub"), rows of X staged through shared memory with
     cp.async ("spmm_stage"), and the work-item table that replaces the binary search ("spmm_segmeta", default on).
     Every variant sums a row in the same order: switching them must not change a bit of the influence matrix."""
@@ -80,7 +80,14 @@ def test_large_spmm_variants_give_the_same_bits(large):
     with ops.option("spmm_segmeta", 0), ops.profile() as prof0:
         searched = run()
     assert "spmm_hub_prepare" not in prof0.report()
-    for name, t in (("hub", hub), ("staged", staged), ("hub+staged", both), ("binary search", searched)):
+    # L2 eviction-priority hints derived from the entry values (default on, threshold measured from the degree
+    # histogram): they steer caching only
+    with ops.option("spmm_hint", 0):
+        unhinted = run()
+    with ops.option("spmm_hint", 1), ops.option("spmm_hint_deg", 37):
+        hinted = run()
+    for name, t in (("hub", hub), ("staged", staged), ("hub+staged", both), ("binary search", searched),
+                    ("no hints", unhinted), ("other hints", hinted)):
         assert bool(torch.equal(t, infl)), name
 
 
