@@ -470,6 +470,8 @@ def main():
             "config": bench_config(wl.describe(), world),
             "l2_flush_between_steps": bool(flush), "options": list(args.opt), "exchange": exchange,
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+            "library_options": {k: ops.get_option(k) for k in ("overlap", "sign_path", "tc_ws", "spmm_hint", "spmm_hint_deg",
+                                                               "spmm_hub", "spmm_segmeta", "shard_rows", "fix_eps")},
             "roofline": roofline, "roofline_frontier": roofline_frontier,
             "phases_ms_per_step": {k: round(v, 4) for k, v in per_step.items()},
             "plan": {k: int(v) for k, v in info.items()},
