@@ -274,6 +274,13 @@ def test_a8_errors(ops, golden):
         ops.attack_efficient(hat, x, w1, b1, w2, dev(np.array([1, 2, 1], np.int32)), DELTA)
     with pytest.raises(RuntimeError, match="outside"):
         ops.attack_efficient(hat, x, w1, b1, w2, dev(np.array([1, s.n], np.int32)), DELTA)
+    # δ = 0 would make every entry NaN, a row stride below T would overrun the caller's buffer: both refused up front
+    tn = dev(g["a6_test_nodes"].astype(np.int32))
+    with pytest.raises(RuntimeError, match="delta must not be 0"):
+        ops.attack_efficient(hat, x, w1, b1, w2, tn, 0.0)
+    with pytest.raises(RuntimeError, match="ldo"):
+        ops.attack_efficient(hat, x, w1, b1, w2, tn, DELTA,
+                             out=torch.empty((tn.numel(), tn.numel() - 1), dtype=torch.float32, device="cuda"))
     # asymmetric pattern is refused (the rank-1 column = row shortcut needs symmetry)
     ip, ix, v = O.coo_to_csr(g["a2_row"], g["a2_col"], g["a2_val"], s.n)
     A = sp.csr_matrix((v, ix, ip), shape=(s.n, s.n)).tolil()
