@@ -113,3 +113,17 @@ def test_config_twitch_three_layers():
     # the same rows through the sharding entry point, as two ranks would compute them
     part = ops.attack_rows(wl.adj_hat, wl.x, wd, wl.test_nodes, wl.delta, lo=250, hi=500)
     assert np.array_equal(part.cpu().numpy(), infl[250:500])
+
+
+def test_more_test_nodes_than_one_tile_of_the_plan_head():
+    """The plan head scans the test-node lengths in tiles of 8192 with a running carry (k_test_lens_scan).  An entry
+    influence[i][j] depends on v_i, v_j and the graph only, and its sum runs over the shared neighbours in node order,
+    so the matrix of the first 8192 test nodes must reappear BIT FOR BIT inside the matrix of 10 000."""
+    from linkteller_b200 import ops, workloads
+    wl = workloads.make("flickr", n_test=10000)
+    big = ops.attack_efficient(wl.adj_hat, wl.x, wl.w1, wl.b1, wl.w2, wl.test_nodes, wl.delta)
+    small = ops.attack_efficient(wl.adj_hat, wl.x, wl.w1, wl.b1, wl.w2, wl.test_nodes[:8192].contiguous(), wl.delta)
+    assert bool(torch.equal(big[:8192, :8192], small))
+    tail = ops.attack_efficient(wl.adj_hat, wl.x, wl.w1, wl.b1, wl.w2, wl.test_nodes[8192:].contiguous(), wl.delta)
+    assert bool(torch.equal(big[8192:, 8192:], tail))
+    assert int((big != 0).sum()) > int((small != 0).sum()) + int((tail != 0).sum())      # and the cross blocks are populated
